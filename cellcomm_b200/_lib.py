@@ -1,0 +1,132 @@
+"""ctypes binding of libcellcomm_b200.so (the C ABI declared in include/cellcomm_b200.h).
+
+There is no CPU fallback: if the shared library cannot be found/built, `load()` raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i32, c_i64, c_u32, c_u64, c_f32 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
+vp = C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    """cc_gemm_desc"""
+    _fields_ = [
+        ("M", c_i32), ("N", c_i32),
+        ("a_mn_major", c_i32), ("b_mn_major", c_i32),
+        ("nseg", c_i32),
+        ("a", vp * 3), ("lda", c_i64 * 3),
+        ("b", vp * 3), ("ldb", c_i64 * 3),
+        ("k", c_i32 * 3),
+        ("alpha", c_f32),
+        ("bias", vp), ("act", c_i32),
+        ("dact_y", vp), ("ld_dact", c_i64), ("dact", c_i32),
+        ("out16", vp), ("ld16", c_i64), ("beta16", c_i32),
+        ("out32", vp), ("ld32", c_i64), ("beta32", c_i32),
+        ("workspace", vp), ("workspace_elems", c_i64),
+        ("force_splits", c_i32), ("force_bn", c_i32),
+        ("reserved", c_i32 * 6),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/cellcomm_b200.h declares
+SIGNATURES = {
+    "cc_last_error": (C.c_char_p, []),
+    "cc_version": (C.c_int, []),
+    "cc_launch_count": (C.c_longlong, []),
+    "cc_arch": (C.c_char_p, []),
+    "cc_mtx_load_csr": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "cc_coo_to_csr": (C.c_int, [vp, vp, vp, c_i64, C.POINTER(vp)]),
+    "cc_csr_destroy": (None, [vp]),
+    "cc_csr_rows": (c_i64, [vp]),
+    "cc_csr_cols": (c_i64, [vp]),
+    "cc_csr_nnz": (c_i64, [vp]),
+    "cc_csr_rowptr": (vp, [vp]),
+    "cc_csr_colidx": (vp, [vp]),
+    "cc_csr_values": (vp, [vp]),
+    "cc_csr_values64": (vp, [vp]),
+    "cc_csr_row_ids": (vp, [vp]),
+    "cc_csr_col_ids": (vp, [vp]),
+    "cc_gather_rows": (C.c_int, [vp, vp, vp, vp, c_i64, c_i64, c_i64, vp, c_i64, vp, c_i64, vp]),
+    "cc_gemm": (C.c_int, [C.POINTER(GemmDesc), vp]),
+    "cc_gemm_workspace_elems": (c_i64, [c_i32, c_i32]),
+    "cc_dense_fwd": (C.c_int, [c_i32, c_i32, c_i32, C.POINTER(vp), C.POINTER(c_i64),
+                               C.POINTER(c_i32), C.POINTER(vp), C.POINTER(c_i64), vp, c_i32,
+                               vp, c_i64, vp, c_i64, vp, c_i64, vp]),
+    "cc_dense_dgrad": (C.c_int, [c_i32, c_i32, c_i32, C.POINTER(vp), C.POINTER(c_i64),
+                                 C.POINTER(c_i32), C.POINTER(vp), C.POINTER(c_i64), vp, c_i64,
+                                 c_i32, c_f32, vp, c_i64, c_i32, vp, c_i64, vp]),
+    "cc_dense_wgrad": (C.c_int, [c_i32, c_i32, c_i32, vp, c_i64, vp, c_i64, vp, c_i64, c_i32, vp]),
+    "cc_colsum": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, vp]),
+    "cc_dropout": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp, c_i64, c_u64, vp,
+                             c_u32, vp]),
+    "cc_dropout_mask": (C.c_int, [vp, c_i64, c_i64, c_i64, c_f32, c_u64, vp, c_u32, vp]),
+    "cc_uniform": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, c_u64, vp, c_u32, vp]),
+    "cc_counter_add": (C.c_int, [vp, c_u64, vp]),
+    "cc_act_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
+    "cc_copy2d": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
+    "cc_cast_f32_to_bf16": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_cast_bf16_to_f32": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp]),
+    "cc_bn_stats": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, vp]),
+    "cc_bn_train_apply": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, c_i64, vp, vp, c_f32,
+                                    c_f32, vp, vp, vp, vp, vp]),
+    "cc_bn_infer": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp, c_f32, vp]),
+    "cc_bn_bwd_stats": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp]),
+    "cc_bn_bwd_apply": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp,
+                                  c_i64, vp, vp, vp]),
+    "cc_bn_infer_bwd": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, c_f32, vp]),
+    "cc_softmax_fwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_softmax_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_bce_fwd_bwd": (C.c_int, [vp, c_i64, c_i64, c_i32, c_f32, c_i64, vp, vp, c_i64, vp]),
+    "cc_mse_fwd_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i64, vp, vp,
+                                 c_i64, vp]),
+    "cc_round_half_even": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_argmax_onehot": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_rmsprop_step": (C.c_int, [vp, vp, vp, vp, vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
+                                  c_f32, c_f32, vp]),
+    "cc_bias_act": (C.c_int, [vp, c_i32, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+    "cc_fill_f32": (C.c_int, [vp, c_f32, c_i64, vp]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first when stale and nvcc is present) the C-ABI library.  Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if os.environ.get("CELLCOMM_B200_NO_BUILD") != "1":
+        try:
+            if _build.is_stale():
+                _build.build_library()
+        except Exception as exc:  # no nvcc on this box: fall through to the prebuilt file
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"libcellcomm_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise RuntimeError(f"libcellcomm_b200.so not found at {path}; run "
+                           f"`python -m cellcomm_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class CCError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise CCError(load().cc_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,646 @@
+// tcgen05 / TMEM / TMA bf16 GEMM with fused epilogue for sm_100a.
+//
+// D[M,N] = epi( sum_s A_s[M,K_s] * B_s[K_s,N] )         (see include/cellcomm_b200.h)
+//
+// Replaces the Dense matmuls TensorFlow's CPU runtime executes for
+// Model.train_on_batch / Model.predict in the reference
+// (src/bigan_classify.py:10-75,144-155, src/bigan_cont.py:7-41).
+//
+// Structure (one 128 x BN output tile per CTA, 128 threads, 2 CTAs per SM so one
+// CTA's epilogue overlaps the other's main loop):
+//   warp 0 : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier tx)
+//   warp 1 : tcgen05.mma issuer (single elected lane), owns TMEM alloc/dealloc
+//   warps 0-3 : epilogue    (tcgen05.ld 32x32b -> registers -> global)
+// Operands can be K-major or MN-major (UMMA "major" bits), so forward
+// (A K-major, B MN-major), dgrad (K,K) and wgrad (MN,MN) all read the same
+// row-major tensors with no transposes.
+// Split-K: gridDim.z CTAs each accumulate a k-block range and write fp32
+// partials; splitk_finalize applies the epilogue.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace cc {
+
+constexpr int BM = 128;     // tile rows  (UMMA M, cta_group::1)
+constexpr int BK = 64;      // k-block: 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;  // fixed for 16-bit inputs
+constexpr int MAX_SEG = 3;
+
+struct EpiParams {
+  int M, N;
+  float alpha;
+  const float* bias;
+  int act;
+  const bf16* dact_y;
+  long long ld_dact;
+  int dact;
+  bf16* out16;
+  long long ld16;
+  int beta16;
+  float* out32;
+  long long ld32;
+  int beta32;
+};
+
+struct GemmParams {
+  EpiParams epi;
+  int nseg;
+  int kblocks[MAX_SEG];  // k-blocks per segment
+  int total_kblocks;
+  int kb_per_split;      // k-blocks handled by one blockIdx.z
+  float* partial;        // split-K partials [splits][Mpad][Npad] or nullptr
+  long long partial_ld;      // Npad
+  long long partial_stride;  // Mpad*Npad
+  // smem matrix descriptor templates (everything except the start address)
+  unsigned long long adesc_hi, bdesc_hi;
+  unsigned int a_kstep, b_kstep;  // bytes to advance the start address per UMMA_K
+  unsigned int idesc;
+};
+
+struct TmaMaps {
+  CUtensorMap a[MAX_SEG];
+  CUtensorMap b[MAX_SEG];
+};
+
+// ----------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (recoverable) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins == 4096u) t0 = clock64();
+    if (spins > 4096u && (spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("cc_gemm: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// --------------------------------------------------------------- epilogue math
+// One thread owns 32 consecutive columns [c0, c0+32) of row r.
+__device__ __forceinline__ void epilogue_store32(const EpiParams& e, int r, int c0, float (&v)[32]) {
+  if (r >= e.M) return;
+  const int ncols = min(32, e.N - c0);
+  if (ncols <= 0) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = v[j] * e.alpha;
+    if (e.bias != nullptr && j < ncols) x += __ldg(e.bias + c0 + j);
+    if (e.act == CC_ACT_SIGMOID) x = sigmoidf_(x);
+    else if (e.act == CC_ACT_RELU) x = fmaxf(x, 0.f);
+    v[j] = x;
+  }
+  if (e.dact != 0) {
+    const bf16* yrow = e.dact_y + (long long)r * e.ld_dact + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        float y = bf2f(yrow[j]);
+        v[j] *= (e.dact == CC_ACT_SIGMOID) ? y * (1.f - y) : (y > 0.f ? 1.f : 0.f);
+      }
+    }
+  }
+  if (e.out32 != nullptr) {
+    float* o = e.out32 + (long long)r * e.ld32 + c0;
+    if (ncols == 32 && (((uintptr_t)o) & 15) == 0 && !e.beta32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = e.beta32 ? o[j] + v[j] : v[j];
+    }
+  }
+  if (e.out16 != nullptr) {
+    bf16* o = e.out16 + (long long)r * e.ld16 + c0;
+    if (ncols == 32 && (((uintptr_t)o) & 15) == 0 && !e.beta16) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&p0);
+        u.y = *reinterpret_cast<uint32_t*>(&p1);
+        u.z = *reinterpret_cast<uint32_t*>(&p2);
+        u.w = *reinterpret_cast<uint32_t*>(&p3);
+        *reinterpret_cast<uint4*>(o + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) o[j] = f2bf(e.beta16 ? bf2f(o[j]) + v[j] : v[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------- kernel
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(128, 2)
+gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN;  // fp32 accumulator: one column per N
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024B-aligned tiles
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full, then tmem ptr slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.total_kblocks, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int seg = 0, kb_in_seg = kb_begin;
+    while (seg < p.nseg - 1 && kb_in_seg >= p.kblocks[seg]) {
+      kb_in_seg -= p.kblocks[seg];
+      ++seg;
+    }
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u, 1);
+      if (lane == 0) {
+        const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+        const uint32_t b_dst = a_dst + A_BYTES;
+        const int k0 = kb_in_seg * BK;
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        if (A_MN) {
+          // A stored [K, M]: inner = M.  Two 64-wide boxes of BK rows each.
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0);
+        } else {
+          // A stored [M, K]: inner = K.  One box 64(K) x 128(M).
+          tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
+        } else {
+          tma_load_2d(b_dst, &maps.b[seg], full_bar(s), k0, n0);
+        }
+      }
+      __syncwarp();
+      if (++kb_in_seg >= p.kblocks[seg] && seg < p.nseg - 1) {
+        kb_in_seg = 0;
+        ++seg;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph, 2);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_src = smem_base + s * STAGE_BYTES;
+        const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = p.adesc_hi | (uint64_t)(((a_src + k * p.a_kstep) & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = p.bdesc_hi | (uint64_t)(((b_src + k * p.b_kstep) & 0x3FFFFu) >> 4);
+          umma_bf16(tmem_acc, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees this smem stage when the MMAs retire
+        if (i == nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ===================== epilogue (all 4 warps) =====================
+  mbar_wait(tmem_full_bar, 0, 3);
+  tcgen05_fence_after();
+  {
+    const int r = m0 + warp * 32 + lane;
+    const uint32_t t_row = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const bool split = (p.partial != nullptr);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.epi.N) break;  // warp-uniform
+      uint32_t raw[32];
+      tmem_ld32(t_row + (uint32_t)c, raw);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (split) {
+        if (r < p.epi.M) {
+          float* o = p.partial + (long long)blockIdx.z * p.partial_stride +
+                     (long long)r * p.partial_ld + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      } else {
+        epilogue_store32(p.epi, r, n0 + c, v);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// Sum split-K partials and apply the epilogue.  One thread per (row, 32-col chunk).
+__global__ void splitk_finalize_kernel(const EpiParams e, const float* __restrict__ partial,
+                                       long long partial_ld, long long partial_stride, int splits) {
+  const int chunks = (e.N + 31) / 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)e.M * chunks) return;
+  const int r = (int)(idx / chunks);
+  const int c0 = (int)(idx % chunks) * 32;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* src = partial + (long long)s * partial_stride + (long long)r * partial_ld + c0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 q = *reinterpret_cast<const float4*>(src + j);
+      v[j] += q.x;
+      v[j + 1] += q.y;
+      v[j + 2] += q.z;
+      v[j + 3] += q.w;
+    }
+  }
+  epilogue_store32(e, r, c0, v);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld &&
+           box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= k.inner + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.outer + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.ld + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= ((uint64_t)k.box_inner << 32 | k.box_outer) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+
+// bf16 row-major [outer, inner] tensor with leading dimension ld (elements).
+static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  CC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  CC_REQUIRE(((uintptr_t)ptr & 15) == 0, "cc_gemm: operand base %p is not 16-byte aligned", ptr);
+  CC_REQUIRE((ld * 2) % 16 == 0, "cc_gemm: operand ld=%llu is not a multiple of 8 elements",
+             (unsigned long long)ld);
+  CC_REQUIRE(inner > 0 && outer > 0, "cc_gemm: empty operand");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CC_REQUIRE(r == CUDA_SUCCESS,
+             "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
+             (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer,
+             (unsigned long long)ld, box_inner, box_outer);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > (1u << 16)) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+// smem matrix descriptor without the start address (cute::UMMA::SmemDescriptor):
+//   [16,30) leading byte offset >>4, [32,46) stride byte offset >>4,
+//   [46,48) version = 1, [61,64) layout type (2 = SWIZZLE_128B)
+static uint64_t desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int BN, int STAGES>
+static constexpr size_t smem_bytes() {
+  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 2) + 1024;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_cfg(const TmaMaps& maps, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  constexpr size_t smem = smem_bytes<BN, STAGES>();
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<grid, 128, smem, st>>>(maps, p);
+  CC_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_major(const TmaMaps& maps, const GemmParams& p, dim3 grid, bool a_mn, bool b_mn,
+                        cudaStream_t st) {
+  if (!a_mn && b_mn) return launch_cfg<BN, STAGES, false, true>(maps, p, grid, st);
+  if (!a_mn && !b_mn) return launch_cfg<BN, STAGES, false, false>(maps, p, grid, st);
+  if (a_mn && b_mn) return launch_cfg<BN, STAGES, true, true>(maps, p, grid, st);
+  return launch_cfg<BN, STAGES, true, false>(maps, p, grid, st);
+}
+
+static int g_num_sms = 0;
+
+int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
+  CC_REQUIRE(d != nullptr, "cc_gemm: null descriptor");
+  CC_REQUIRE(d->M > 0 && d->N > 0, "cc_gemm: empty output %dx%d", d->M, d->N);
+  CC_REQUIRE(d->nseg >= 1 && d->nseg <= MAX_SEG, "cc_gemm: nseg=%d out of range", d->nseg);
+  CC_REQUIRE(d->out16 != nullptr || d->out32 != nullptr, "cc_gemm: no output");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CC_CHECK_CUDA(cudaGetDevice(&dev));
+    CC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;
+
+  int bn = d->force_bn ? d->force_bn : env_int("CC_GEMM_BN", 0);
+  if (bn == 0) bn = (d->N > 128) ? 256 : 128;
+  CC_REQUIRE(bn == 128 || bn == 256, "cc_gemm: BN=%d unsupported", bn);
+
+  GemmParams p{};
+  TmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.nseg = d->nseg;
+  int total = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    CC_REQUIRE(d->k[s] > 0, "cc_gemm: segment %d has k=%d", s, d->k[s]);
+    p.kblocks[s] = (d->k[s] + BK - 1) / BK;
+    total += p.kblocks[s];
+    int rc;
+    if (a_mn)  // stored [K, M]
+      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->M, (uint64_t)d->k[s], (uint64_t)d->lda[s], 64, BK);
+    else  // stored [M, K]
+      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->k[s], (uint64_t)d->M, (uint64_t)d->lda[s], BK, BM);
+    if (rc) return rc;
+    if (b_mn)  // stored [K, N]
+      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->N, (uint64_t)d->k[s], (uint64_t)d->ldb[s], 64, BK);
+    else  // stored [N, K]
+      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->k[s], (uint64_t)d->N, (uint64_t)d->ldb[s], BK, (uint32_t)bn);
+    if (rc) return rc;
+  }
+  p.total_kblocks = total;
+
+  // UMMA descriptors.  K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=16B),
+  // K advance = 32 B inside the swizzle row.  MN-major, 128B swizzle: 64-element MN atoms are
+  // separate TMA boxes 64*BK*2 = 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance =
+  // 16 rows * 128 B.
+  const uint32_t mn_lbo = (uint32_t)env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
+  const uint32_t mn_sbo = (uint32_t)env_int("CC_GEMM_MN_SBO", 1024);
+  const uint32_t mn_kstep = (uint32_t)env_int("CC_GEMM_MN_KSTEP", UMMA_K * 128);
+  const uint32_t k_lbo = (uint32_t)env_int("CC_GEMM_K_LBO", 16);
+  const uint32_t k_sbo = (uint32_t)env_int("CC_GEMM_K_SBO", 1024);
+  p.adesc_hi = a_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
+  p.bdesc_hi = b_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
+  p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
+  p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
+  // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+  // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
+            ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  EpiParams& e = p.epi;
+  e.M = d->M;
+  e.N = d->N;
+  e.alpha = d->alpha;
+  e.bias = d->bias;
+  e.act = d->act;
+  e.dact_y = (const bf16*)d->dact_y;
+  e.ld_dact = d->ld_dact;
+  e.dact = d->dact_y ? d->dact : 0;
+  e.out16 = (bf16*)d->out16;
+  e.ld16 = d->ld16;
+  e.beta16 = d->beta16;
+  e.out32 = d->out32;
+  e.ld32 = d->ld32;
+  e.beta32 = d->beta32;
+
+  const int mt = (d->M + BM - 1) / BM, nt = (d->N + bn - 1) / bn;
+  // split-K when the tile grid cannot fill the machine and the reduction is long
+  int splits = 1;
+  const long long Mpad = (long long)mt * BM, Npad = (long long)nt * bn;
+  if (d->workspace != nullptr) {
+    int want = d->force_splits ? d->force_splits : env_int("CC_GEMM_SPLITS", 0);
+    if (want == 0) {
+      const int tiles = mt * nt;
+      const int slots = 2 * g_num_sms;
+      if (tiles < slots && total >= 8) {
+        want = (slots + tiles - 1) / tiles;
+        if (want > total / 4) want = total / 4;
+      } else {
+        want = 1;
+      }
+    }
+    if (want > total) want = total;
+    const long long cap = d->workspace_elems / (Mpad * Npad);
+    if (want > cap) want = (int)cap;
+    if (want >= 2) splits = want;
+  }
+  p.kb_per_split = (total + splits - 1) / splits;
+  splits = (total + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  if (splits >= 2) {
+    p.partial = d->workspace;
+    p.partial_ld = Npad;
+    p.partial_stride = Mpad * Npad;
+  } else {
+    p.partial = nullptr;
+    p.kb_per_split = total;
+    splits = 1;
+  }
+
+  dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
+  int rc;
+  if (bn == 256)
+    rc = launch_major<256, 2>(maps, p, grid, a_mn, b_mn, st);
+  else
+    rc = launch_major<128, 3>(maps, p, grid, a_mn, b_mn, st);
+  if (rc) return rc;
+  if (splits >= 2) {
+    const long long work = (long long)d->M * ((d->N + 31) / 32);
+    const int threads = 128;
+    splitk_finalize_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(
+        p.epi, p.partial, p.partial_ld, p.partial_stride, splits);
+    CC_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace cc
+
+extern "C" int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream) {
+  return cc::gemm_impl(desc, (cudaStream_t)stream);
+}
+
+extern "C" int64_t cc_gemm_workspace_elems(int32_t M, int32_t N) {
+  // room for up to 2*148 CTAs' worth of 128x256 fp32 partial tiles, or 8 splits of the padded
+  // output, whichever is larger
+  const long long Mpad = ((long long)M + 127) / 128 * 128, Npad = ((long long)N + 255) / 256 * 256;
+  long long a = 296LL * 128 * 256 * 2;
+  long long b = 8 * Mpad * Npad;
+  return a > b ? a : b;
+}

@@ -1,0 +1,755 @@
+"""Network graphs + forward/backward executor over the C-ABI kernels.
+
+This is the host side of what TensorFlow/Keras does for the reference inside
+`Model.train_on_batch` / `Model.predict` (src/bigan_classify.py:83-155): a static layer graph
+per network (G, E, D), a forward pass that saves activations, a reverse pass that emits
+dgrad / wgrad GEMMs and the tail kernels, and a fused-layout RMSprop update.  All arithmetic
+is in libcellcomm_b200.so (cellcomm_b200.ops); torch only owns buffers and streams.
+
+Semantics follow Keras 2.4.0 as used by the reference:
+  * Dense: y = act(x W + b), W[in,out]; Concatenate inputs are consumed as GEMM segments.
+  * BatchNormalization: eps 1e-3, momentum 0.99, biased batch variance; a frozen
+    (trainable=False) BN runs in inference mode even inside train_on_batch.
+  * Dropout: active inside frozen sub-models during train_on_batch, off in predict.
+"""
+import math
+
+import torch
+
+from . import ops as _ops_module
+
+# tests may swap this for an emulator to exercise the host logic without a GPU
+ops = _ops_module
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.99                  # Keras BatchNormalization defaults
+LR, RHO, MOMENTUM, EPSILON = 0.0075, 0.85, 0.1, 1e-7   # src/bigan_classify.py:88 (+ Keras eps)
+REAL_LABEL = 0.95                                 # src/bigan_classify.py:128
+
+_ACT = {"none": 0, "sigmoid": 1, "relu": 2, "softmax": 0}
+
+
+# =========================================================================== graph specs
+class GraphBuilder:
+    """Records a network as nodes over tensor ids; layers keep the reference's creation order."""
+
+    def __init__(self, name):
+        self.name = name
+        self.widths = []
+        self.nodes = []
+        self.inputs = {}
+        self.layers = []       # ("dense", in_widths, units, act) | ("bn", width)
+        self.n_dropout = 0
+        self.output = None
+
+    def _new(self, width):
+        self.widths.append(int(width))
+        return len(self.widths) - 1
+
+    def input(self, name, width):
+        t = self._new(width)
+        self.inputs[name] = t
+        return t
+
+    def dense(self, ins, units, act):
+        ins = list(ins) if isinstance(ins, (list, tuple)) else [ins]
+        out = self._new(units)
+        self.layers.append(("dense", [self.widths[i] for i in ins], int(units), act))
+        self.nodes.append({"kind": "dense", "ins": ins, "out": out, "layer": len(self.layers) - 1,
+                           "act": act})
+        if act == "softmax":
+            sm = self._new(units)
+            self.nodes.append({"kind": "softmax", "ins": [out], "out": sm})
+            return sm
+        return out
+
+    def bn(self, x):
+        out = self._new(self.widths[x])
+        self.layers.append(("bn", self.widths[x]))
+        self.nodes.append({"kind": "bn", "ins": [x], "out": out, "layer": len(self.layers) - 1})
+        return out
+
+    def dropout(self, x, rate):
+        out = self._new(self.widths[x])
+        self.nodes.append({"kind": "dropout", "ins": [x], "out": out, "rate": float(rate),
+                           "drop": self.n_dropout})
+        self.n_dropout += 1
+        return out
+
+    def concat(self, xs):
+        out = self._new(sum(self.widths[i] for i in xs))
+        self.nodes.append({"kind": "concat", "ins": list(xs), "out": out})
+        return out
+
+
+def cont_generator_graph(Z, G):
+    """src/bigan_cont.py:7-25"""
+    w = [int(G * f) for f in (0.2, 0.1)]
+    b = GraphBuilder("cell_generator")
+    z, r = b.input("z", Z), b.input("r", Z)
+    all_in = b.concat([z, r])
+    x = b.dense(all_in, 50, "sigmoid")
+    x = b.dropout(b.concat([x, all_in]), 0.1)
+    x = b.dense(x, 256, "sigmoid")
+    x = b.dense(x, 256, "sigmoid")
+    x = b.bn(x)
+    x = b.dropout(b.concat([x, all_in]), 0.1)
+    x = b.dense(x, w[1], "sigmoid")
+    x = b.dense(x, w[0], "relu")
+    x = b.bn(x)
+    b.output = b.dense(x, G, "relu")
+    return b
+
+
+def cont_encoder_graph(Z, G):
+    """src/bigan_cont.py:28-41"""
+    w = [int(G * f) for f in (0.1, 0.05)]
+    b = GraphBuilder("cell_encoder")
+    cell = b.input("cell", G)
+    x = b.dense(cell, w[0], "sigmoid")
+    x = b.dropout(x, 0.15)
+    x = b.dense([x, cell], w[1], "sigmoid")      # Concatenate()([x, cell_in]) as two GEMM segments
+    x = b.dropout(x, 0.1)
+    x = b.bn(x)
+    x = b.dense(x, 150, "sigmoid")
+    x = b.dense(x, 150, "sigmoid")
+    b.output = b.dense(x, Z, "sigmoid")
+    return b
+
+
+def classify_generator_graph(Z, G):
+    """src/bigan_classify.py:10-25"""
+    b = GraphBuilder("cell_generator")
+    z, r = b.input("z", Z), b.input("r", Z)
+    all_in = b.concat([z, r])
+    x = b.dense(all_in, 50, "sigmoid")
+    x = b.dropout(b.concat([x, all_in]), 0.1)
+    x = b.dense(x, 256, "sigmoid")
+    x = b.bn(x)
+    x = b.dropout(b.concat([x, all_in]), 0.1)
+    x = b.dense(x, 256, "sigmoid")
+    x = b.dropout(x, 0.1)
+    x = b.dense(x, 1024, "relu")
+    b.output = b.dense(x, G, "relu")
+    return b
+
+
+def classify_encoder_graph(Z, G):
+    """src/bigan_classify.py:28-40"""
+    b = GraphBuilder("cell_encoder")
+    cell = b.input("cell", G)
+    proc = b.dense(cell, 1000, "sigmoid")
+    x = b.dropout(proc, 0.15)
+    x = b.dense(x, 300, "sigmoid")
+    x = b.dropout(x, 0.15)
+    x = b.dense([x, proc], 150, "sigmoid")
+    b.output = b.dense(x, Z, "softmax")
+    return b
+
+
+def discriminator_graph(Z, G):
+    """src/bigan_classify.py:43-75 (shared by both variants, bigan_cont.py:46-50)"""
+    l = [int(G * f) for f in (0.3, 0.1, 0.05)]
+    b = GraphBuilder("cell_discriminator")
+    z, cell = b.input("z", Z), b.input("cell", G)
+    a = b.dense(z, 50, "sigmoid")
+    a2 = b.dense(z, 50, "sigmoid")
+    x = b.dropout(b.concat([a, a2, z]), 0.15)
+    x = b.bn(x)
+    x = b.dense(x, 256, "sigmoid")
+    x = b.dense(x, 256, "sigmoid")
+    se = b.dense(x, 256, "sigmoid")
+    x = b.dense(cell, l[0], "sigmoid")
+    x = b.dropout(x, 0.15)
+    x = b.dense([x, cell], l[1], "sigmoid")
+    x = b.bn(x)
+    x = b.dropout(x, 0.15)
+    x = b.dense(x, l[2], "sigmoid")
+    x = b.dense(x, 256, "sigmoid")
+    sg = b.dense(x, 256, "sigmoid")
+    x = b.dense([se, sg], 300, "sigmoid")
+    x = b.bn(x)
+    x = b.dropout(x, 0.15)
+    x = b.dense(x, 50, "sigmoid")
+    x = b.dense(x, 50, "sigmoid")
+    x = b.dense(x, 10, "sigmoid")
+    b.output = b.dense(x, 1, "sigmoid")
+    return b
+
+
+# =========================================================================== runtime
+def _pad(n, m=64):
+    return (n + m - 1) // m * m
+
+
+class _NoDist:
+    world_size = 1
+
+    def all_reduce(self, t):
+        return t
+
+
+class Net:
+    """One network (G, E or D): parameters in flat fused-layout buffers, activation buffers for
+    up to `max_rows` rows, forward / backward / RMSprop."""
+
+    def __init__(self, graph, max_rows, device, generator=None, dist=None):
+        self.g = graph
+        self.name = graph.name
+        self.max_rows = int(max_rows)
+        self.device = device
+        self.dist = dist or _NoDist()
+        self._alloc_params(generator)
+        self.act = {}
+        self.grad = {}
+        self.tmp = {}
+        self._needs_cache = {}
+        self._ctx = None
+        self.logits32 = None
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self, generator):
+        dev = self.device
+        off = 0
+        meta = []
+        for lay in self.g.layers:
+            if lay[0] == "dense":
+                K, N = sum(lay[1]), lay[2]
+                ldn = ops.pad_ld(N)
+                meta.append({"kind": "dense", "K": K, "N": N, "ld": ldn, "w_off": off,
+                             "b_off": off + K * ldn, "act": lay[3], "in_widths": lay[1]})
+                off += K * ldn + _pad(N)
+            else:
+                n = lay[1]
+                meta.append({"kind": "bn", "n": n, "g_off": off, "be_off": off + _pad(n)})
+                off += 2 * _pad(n)
+        self.n_flat = max(off, 64)
+        self.p32 = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
+        self.g32 = torch.zeros_like(self.p32)
+        self.ms = torch.zeros_like(self.p32)
+        self.mom = torch.zeros_like(self.p32)
+        self.p16 = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)
+        self.layers = []
+        for m in meta:
+            L = dict(m)
+            if m["kind"] == "dense":
+                K, N, ld = m["K"], m["N"], m["ld"]
+                wv = lambda buf: buf[m["w_off"]:m["w_off"] + K * ld].view(K, ld)[:, :N]
+                bv = lambda buf: buf[m["b_off"]:m["b_off"] + N]
+                L.update(w32=wv(self.p32), w16=wv(self.p16), dw=wv(self.g32), b32=bv(self.p32),
+                         db=bv(self.g32))
+                fan = K + N
+                if K > 0 and N > 0:
+                    limit = math.sqrt(6.0 / fan)      # glorot_uniform (Keras Dense default)
+                    u = torch.rand((K, N), generator=generator, dtype=torch.float32)
+                    L["w32"].copy_(((u * 2 - 1) * limit).to(dev))
+            else:
+                n = m["n"]
+                L.update(gamma=self.p32[m["g_off"]:m["g_off"] + n],
+                         beta=self.p32[m["be_off"]:m["be_off"] + n],
+                         dgamma=self.g32[m["g_off"]:m["g_off"] + n],
+                         dbeta=self.g32[m["be_off"]:m["be_off"] + n],
+                         moving_mean=torch.zeros(n, dtype=torch.float32, device=dev),
+                         moving_var=torch.ones(n, dtype=torch.float32, device=dev),
+                         sums=torch.zeros(2 * max(n, 1), dtype=torch.float32, device=dev),
+                         sums2=torch.zeros(2 * max(n, 1), dtype=torch.float32, device=dev),
+                         save_mean=torch.zeros(max(n, 1), dtype=torch.float32, device=dev),
+                         save_rstd=torch.zeros(max(n, 1), dtype=torch.float32, device=dev))
+                L["gamma"].fill_(1.0)
+            self.layers.append(L)
+        self.sync_compute_copy()
+
+    def sync_compute_copy(self):
+        """bf16 compute copy <- fp32 master (after init / set_weights)."""
+        self.p16.copy_(self.p32)
+
+    def param_count(self):
+        n = 0
+        for L in self.layers:
+            n += (L["K"] * L["N"] + L["N"]) if L["kind"] == "dense" else 4 * L["n"]
+        return n
+
+    def trainable_count(self):
+        n = 0
+        for L in self.layers:
+            n += (L["K"] * L["N"] + L["N"]) if L["kind"] == "dense" else 2 * L["n"]
+        return n
+
+    def get_weights(self):
+        """Creation order; Dense -> kernel[in,out], bias; BN -> gamma, beta, mean, var (host)."""
+        out = []
+        for L in self.layers:
+            keys = ("w32", "b32") if L["kind"] == "dense" else (
+                "gamma", "beta", "moving_mean", "moving_var")
+            out += [L[k].detach().float().cpu().numpy().copy() for k in keys]
+        return out
+
+    def set_weights(self, arrays):
+        it = iter(arrays)
+        for L in self.layers:
+            keys = ("w32", "b32") if L["kind"] == "dense" else (
+                "gamma", "beta", "moving_mean", "moving_var")
+            for k in keys:
+                a = torch.as_tensor(next(it), dtype=torch.float32)
+                if tuple(a.shape) != tuple(L[k].shape):
+                    raise ValueError(f"{self.name}: weight shape {tuple(a.shape)} != "
+                                     f"{tuple(L[k].shape)}")
+                if a.numel():
+                    L[k].copy_(a.to(self.device))
+        self.ms.zero_()
+        self.mom.zero_()
+        self.sync_compute_copy()
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, store, tid, dtype=torch.bfloat16):
+        b = store.get(tid)
+        if b is None:
+            b = ops.alloc2d(self.max_rows, self.g.widths[tid], dtype=dtype, device=self.device)
+            store[tid] = b
+        return b
+
+    def _needs(self, train, want):
+        key = (bool(train), tuple(sorted(want)))
+        nd = self._needs_cache.get(key)
+        if nd is None:
+            nd = [False] * len(self.g.widths)
+            for name, t in self.g.inputs.items():
+                nd[t] = name in want
+            for node in self.g.nodes:
+                has_params = node["kind"] in ("dense", "bn")
+                nd[node["out"]] = (train and has_params) or any(nd[i] for i in node["ins"])
+            self._needs_cache[key] = nd
+        return nd
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, feed, rows, *, bn_train, dropout="off", masks=None, rng=None,
+                pre_activation=False, out32=None):
+        """feed: {input name: [rows, width] bf16 view}.  dropout: 'off' (predict), 'masks'
+        (explicit uint8 keep-masks in call order) or 'rng' (rng = (seed, counter, base_id)).
+        Returns the output activation ([rows, width] bf16), or fp32 logits when pre_activation."""
+        if rows > self.max_rows:
+            raise ValueError(f"{self.name}: batch of {rows} rows exceeds max_rows={self.max_rows}")
+        g = self.g
+        A = {}
+        for name, t in g.inputs.items():
+            x = feed[name]
+            if x.shape != (rows, g.widths[t]):
+                raise ValueError(f"{self.name}: input '{name}' has shape {tuple(x.shape)}, "
+                                 f"expected {(rows, g.widths[t])}")
+            A[t] = x
+        n_total = rows * self.dist.world_size
+        last = g.nodes[-1]
+        for node in g.nodes:
+            kind, out = node["kind"], node["out"]
+            width = g.widths[out]
+            if kind == "dense":
+                L = self.layers[node["layer"]]
+                y = self._buf(self.act, out)[:rows]
+                is_last = node is last or (last["kind"] == "softmax" and last["ins"][0] == out)
+                o32 = None
+                act = _ACT[node["act"]]
+                if is_last and pre_activation:
+                    if self.logits32 is None:
+                        self.logits32 = ops.alloc2d(self.max_rows, width, dtype=torch.float32,
+                                                    device=self.device)
+                    o32, act = self.logits32[:rows], 0
+                elif is_last and out32 is not None and last["kind"] != "softmax":
+                    o32 = out32
+                if width > 0:
+                    xs, offs, ro = [], [], 0
+                    for i in node["ins"]:
+                        if g.widths[i] > 0:
+                            xs.append(A[i])
+                            offs.append(ro)
+                        ro += g.widths[i]
+                    if xs:
+                        ops.dense_fwd(xs, L["w16"], offs, L["b32"], act, out16=y, out32=o32)
+                    else:
+                        ops.bias_act(L["b32"], act, rows, out16=y, out32=o32)
+                A[out] = y
+            elif kind == "softmax":
+                y = self._buf(self.act, out)[:rows]
+                if width > 0:
+                    ops.softmax_fwd(A[node["ins"][0]], y16=y, y32=out32)
+                A[out] = y
+            elif kind == "bn":
+                L = self.layers[node["layer"]]
+                x = A[node["ins"][0]]
+                y = self._buf(self.act, out)[:rows]
+                if width > 0:
+                    if bn_train:
+                        ops.bn_stats(x, L["sums"])
+                        self.dist.all_reduce(L["sums"])
+                        ops.bn_train_apply(x, y, L["sums"], n_total, L["gamma"], L["beta"],
+                                           BN_EPS, BN_MOMENTUM, L["moving_mean"], L["moving_var"],
+                                           L["save_mean"], L["save_rstd"])
+                    else:
+                        ops.bn_infer(x, y, L["gamma"], L["beta"], L["moving_mean"],
+                                     L["moving_var"], BN_EPS)
+                A[out] = y
+            elif kind == "dropout":
+                x = A[node["ins"][0]]
+                if dropout == "off":
+                    A[out] = x
+                else:
+                    y = self._buf(self.act, out)[:rows]
+                    if width > 0:
+                        self._dropout(node, x, y, dropout, masks, rng)
+                    A[out] = y
+            elif kind == "concat":
+                y = self._buf(self.act, out)[:rows]
+                c = 0
+                for i in node["ins"]:
+                    w = g.widths[i]
+                    if w > 0:
+                        ops.copy2d(A[i], y[:, c:c + w])
+                    c += w
+                A[out] = y
+        self._ctx = {"rows": rows, "bn_train": bn_train, "dropout": dropout, "masks": masks,
+                     "rng": rng, "A": A, "pre_activation": pre_activation, "n_total": n_total}
+        if pre_activation:
+            return self.logits32[:rows]
+        return A[g.output]
+
+    def _dropout(self, node, x, y, mode, masks, rng):
+        if mode == "masks":
+            m = masks[node["drop"]]
+            if m.shape != x.shape:
+                raise ValueError(f"{self.name}: dropout mask {node['drop']} has shape "
+                                 f"{tuple(m.shape)}, expected {tuple(x.shape)}")
+            ops.dropout(x, y, node["rate"], mask=m)
+        else:
+            seed, counter, base = rng
+            ops.dropout(x, y, node["rate"], seed=seed, counter=counter,
+                        stream_id=base + node["drop"])
+
+    # ------------------------------------------------------------------ backward
+    def _emit(self, tid, rows, state, fn):
+        """Write (first contribution) or accumulate (later ones) a gradient for tensor `tid`."""
+        dst = self._buf(self.grad, tid)[:rows]
+        if not state[tid]:
+            fn(dst)
+            state[tid] = True
+        else:
+            t = self._buf(self.tmp, tid)[:rows]
+            fn(t)
+            ops.copy2d(t, dst, beta=1)
+
+    def backward(self, dout, *, train, want=()):
+        """dout: gradient w.r.t. the output (bf16 [rows, width]); for a pre_activation forward it
+        is the gradient w.r.t. the final layer's logits.  train=True fills this net's parameter
+        gradients; `want` names the inputs whose gradients are returned."""
+        c = self._ctx
+        g, rows, A = self.g, c["rows"], c["A"]
+        needs = self._needs(train, want)
+        state = [False] * len(g.widths)
+        out_t = g.output
+        self._buf(self.grad, out_t)
+        if g.widths[out_t] > 0:
+            ops.copy2d(dout, self.grad[out_t][:rows])
+        state[out_t] = True
+        last = g.nodes[-1]
+        for node in reversed(g.nodes):
+            kind, out = node["kind"], node["out"]
+            if not state[out] or not needs[out]:
+                continue
+            width = g.widths[out]
+            dy = self.grad[out][:rows]
+            if kind == "dense":
+                L = self.layers[node["layer"]]
+                if width == 0:
+                    continue
+                is_last = node is last or (last["kind"] == "softmax" and last["ins"][0] == out)
+                act = _ACT[node["act"]]
+                if act != 0 and not (is_last and c["pre_activation"]):
+                    ops.act_bwd(dy, A[out], dy, act)      # dz in place
+                dz = dy
+                ro = 0
+                for i in node["ins"]:
+                    k = g.widths[i]
+                    if k > 0:
+                        if train:
+                            ops.dense_wgrad(A[i], dz, L["dw"][ro:ro + k])
+                        if needs[i]:
+                            wseg = L["w16"][ro:ro + k]
+                            dst = self._buf(self.grad, i)[:rows]
+                            ops.dense_dgrad([dz], [wseg], dst, beta=1 if state[i] else 0)
+                            state[i] = True
+                    ro += k
+                if train:
+                    ops.colsum(dz, L["db"])
+            elif kind == "softmax":
+                i = node["ins"][0]
+                if width > 0 and needs[i]:
+                    self._emit(i, rows, state, lambda d: ops.softmax_bwd(dy, A[out], d))
+            elif kind == "bn":
+                L = self.layers[node["layer"]]
+                i = node["ins"][0]
+                if width == 0:
+                    continue
+                x = A[i]
+                if c["bn_train"]:
+                    ops.bn_bwd_stats(dy, x, L["save_mean"], L["save_rstd"], L["sums2"])
+                    self.dist.all_reduce(L["sums2"])
+                    if needs[i]:
+                        self._emit(i, rows, state, lambda d: ops.bn_bwd_apply(
+                            dy, x, d, L["gamma"], L["save_mean"], L["save_rstd"], L["sums2"],
+                            c["n_total"], L["dgamma"] if train else None,
+                            L["dbeta"] if train else None))
+                    elif train:
+                        ops.bn_bwd_apply(dy, x, None, L["gamma"], L["save_mean"], L["save_rstd"],
+                                         L["sums2"], c["n_total"], L["dgamma"], L["dbeta"])
+                else:
+                    if train:
+                        raise RuntimeError("training a BatchNormalization in inference mode")
+                    if needs[i]:
+                        self._emit(i, rows, state, lambda d: ops.bn_infer_bwd(
+                            dy, d, L["gamma"], L["moving_var"], BN_EPS))
+            elif kind == "dropout":
+                i = node["ins"][0]
+                if width > 0 and needs[i]:
+                    if c["dropout"] == "off":
+                        self._emit(i, rows, state, lambda d: ops.copy2d(dy, d))
+                    else:
+                        self._emit(i, rows, state, lambda d: self._dropout(
+                            node, dy, d, c["dropout"], c["masks"], c["rng"]))
+            elif kind == "concat":
+                col = 0
+                for i in node["ins"]:
+                    w = g.widths[i]
+                    if w > 0 and needs[i]:
+                        src = dy[:, col:col + w]
+                        dst = self._buf(self.grad, i)[:rows]
+                        ops.copy2d(src, dst, beta=1 if state[i] else 0)
+                        state[i] = True
+                    col += w
+        grads = {}
+        for name in want:
+            t = g.inputs[name]
+            if not state[t]:
+                raise RuntimeError(f"{self.name}: no gradient reached input '{name}'")
+            grads[name] = self.grad[t][:rows]
+        return grads
+
+    # ------------------------------------------------------------------ optimiser
+    def apply_rmsprop(self):
+        """Keras RMSprop(lr=0.0075, rho=0.85, momentum=0.1) over the whole flat parameter
+        buffer in one launch; padding has zero gradient and stays zero.  In data-parallel runs
+        the flat gradient is all-reduced (sum of per-rank partial sums) first."""
+        self.dist.all_reduce(self.g32)
+        ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
+                         EPSILON)
+
+
+class LossScalar:
+    """A loss that stays on the device until someone needs the number (float(), format, print).
+    `CellTraining.run` sums these per iteration (src/cell_type_training.py:45-48) without a
+    host sync per step."""
+
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+    def __float__(self):
+        return float(self.t)
+
+    def item(self):
+        return float(self.t)
+
+    def _v(self, o):
+        return o.t if isinstance(o, LossScalar) else o
+
+    def __add__(self, o):
+        return LossScalar(self.t + self._v(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return LossScalar(self.t - self._v(o))
+
+    def __mul__(self, o):
+        return LossScalar(self.t * self._v(o))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return LossScalar(self.t / self._v(o))
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return repr(float(self))
+
+    def __lt__(self, o):
+        return float(self) < float(o)
+
+    def __gt__(self, o):
+        return float(self) > float(o)
+
+    def __eq__(self, o):
+        return float(self) == float(o)
+
+    def __hash__(self):
+        return id(self)
+
+
+class BiGanEngine:
+    """G, E, D plus the eight sub-steps of `trainings_step` (src/bigan_classify.py:126-155)."""
+
+    SUBSTEP_NETS = {1: ("G", "D"), 2: ("E", "G"), 3: ("E", "D"), 4: ("G", "E"), 6: ("D",),
+                    8: ("D",)}
+
+    def __init__(self, variant, encoding_size, gene_size, max_batch=128, device="cuda", seed=None,
+                 dist=None):
+        if variant not in ("cont", "classify"):
+            raise ValueError(f"unknown variant {variant}")
+        self.variant, self.Z, self.Gn = variant, int(encoding_size), int(gene_size)
+        self.device = torch.device(device)
+        self.max_batch = int(max_batch)
+        self.dist = dist or _NoDist()
+        gen = torch.Generator()
+        if seed is None:
+            gen.seed()
+        else:
+            gen.manual_seed(int(seed))
+        gg = cont_generator_graph if variant == "cont" else classify_generator_graph
+        eg = cont_encoder_graph if variant == "cont" else classify_encoder_graph
+        self.G = Net(gg(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
+        self.E = Net(eg(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
+        self.D = Net(discriminator_graph(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
+        self.nets = {"G": self.G, "E": self.E, "D": self.D}
+        self.loss_buf = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
+        self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        mb, Z, Gn = self.max_batch, self.Z, self.Gn
+        self.z16 = ops.alloc2d(mb, Z, device=self.device)
+        self.r16 = ops.alloc2d(mb, Z, device=self.device)
+        self.z32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
+        self.r32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
+        self.dz1 = ops.alloc2d(mb, 1, device=self.device)
+        self.dgen = None
+        self.denc = ops.alloc2d(mb, Z, device=self.device)
+        self.gen_cells = None
+        self.gen_enc16 = ops.alloc2d(mb, Z, device=self.device)
+        self.gen_enc32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ helpers
+    def _drop_args(self, substep, net, masks):
+        if masks is not None:
+            return {"dropout": "masks", "masks": masks[substep][net]}
+        base = substep * 16 + {"G": 0, "E": 4, "D": 8}[net]
+        return {"dropout": "rng", "rng": (self.rng_seed, self.rng_counter, base)}
+
+    def set_latents(self, encodings, noise, rows):
+        """Stage the step's prior samples (host or device, fp32) as fp32 + bf16 device views."""
+        z32, r32 = self.z32[:rows], self.r32[:rows]
+        z32.copy_(torch.as_tensor(encodings, dtype=torch.float32), non_blocking=True)
+        r32.copy_(torch.as_tensor(noise, dtype=torch.float32), non_blocking=True)
+        ops.cast_f32_to_bf16(z32, self.z16[:rows])
+        ops.cast_f32_to_bf16(r32, self.r16[:rows])
+
+    def draw_latents(self, rows):
+        """tf.random.uniform priors on the device (src/bigan_basic.py:36-37, bigan_cont.py:52-53)."""
+        ops.uniform(out32=self.z32[:rows], out16=self.z16[:rows], seed=self.rng_seed,
+                    counter=self.rng_counter, stream_id=1000)
+        ops.uniform(out32=self.r32[:rows], out16=self.r16[:rows], seed=self.rng_seed,
+                    counter=self.rng_counter, stream_id=1001)
+
+    # ------------------------------------------------------------------ the step
+    def train_step(self, x16, masks=None):
+        """One `trainings_step` on the batch x16 ([B, gene_size] bf16 view).  The priors must
+        have been staged with set_latents()/draw_latents().  Returns (g, e, d) LossScalars."""
+        B = x16.shape[0]
+        z, r = self.z16[:B], self.r16[:B]
+        G, E, D = self.G, self.E, self.D
+        n_total = B * self.dist.world_size
+        L = self.loss_buf
+        ops.fill_f32(L, 0.0)
+        if self.dgen is None:
+            self.dgen = ops.alloc2d(self.max_batch, self.Gn, device=self.device)
+            self.gen_cells = ops.alloc2d(self.max_batch, self.Gn, device=self.device)
+        dz1, dgen, denc = self.dz1[:B], self.dgen[:B], self.denc[:B]
+
+        # (1) _train_gen_w_discr.train_on_batch((encodings, noise), y_ones)   bigan_classify.py:145
+        gen = G.forward({"z": z, "r": r}, B, bn_train=True, **self._drop_args(1, "G", masks))
+        logit = D.forward({"z": z, "cell": gen}, B, bn_train=False, pre_activation=True,
+                          **self._drop_args(1, "D", masks))
+        ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[0:1], dz1)
+        dcell = D.backward(dz1, train=False, want=("cell",))["cell"]
+        G.backward(dcell, train=True)
+        G.apply_rmsprop()
+
+        # (2) _train_gen_w_enc.train_on_batch((cell_data, noise), cell_data)  :146
+        enc = E.forward({"cell": x16}, B, bn_train=False, **self._drop_args(2, "E", masks))
+        gen = G.forward({"z": enc, "r": r}, B, bn_train=True, **self._drop_args(2, "G", masks))
+        ops.mse_fwd_bwd(gen, n_total, L[1:2], target16=x16, dpred16=dgen)
+        G.backward(dgen, train=True)
+        G.apply_rmsprop()
+
+        # (3) _train_enc_w_discr.train_on_batch(cell_data, y_zeros)           :150
+        enc = E.forward({"cell": x16}, B, bn_train=True, **self._drop_args(3, "E", masks))
+        logit = D.forward({"z": enc, "cell": x16}, B, bn_train=False, pre_activation=True,
+                          **self._drop_args(3, "D", masks))
+        ops.bce_fwd_bwd(logit, 0.0, n_total, L[2:3], dz1)
+        dzin = D.backward(dz1, train=False, want=("z",))["z"]
+        E.backward(dzin, train=True)
+        E.apply_rmsprop()
+
+        # (4) _train_enc_w_gen.train_on_batch((encodings, noise), encodings)  :151
+        gen = G.forward({"z": z, "r": r}, B, bn_train=False, **self._drop_args(4, "G", masks))
+        enc = E.forward({"cell": gen}, B, bn_train=True, **self._drop_args(4, "E", masks))
+        ops.mse_fwd_bwd(enc, n_total, L[3:4], target32=self.z32[:B], dpred16=denc)
+        E.backward(denc, train=True)
+        E.apply_rmsprop()
+
+        # (5) generated_cells = generate_cells(encodings, noise)             :136
+        gen = G.forward({"z": z, "r": r}, B, bn_train=False, dropout="off")
+        cells = self.gen_cells[:B]
+        ops.round_half_even(gen, out16=cells)
+
+        # (6) _discriminator.train_on_batch((encodings, generated_cells), y_zeros)   :137
+        logit = D.forward({"z": z, "cell": cells}, B, bn_train=True, pre_activation=True,
+                          **self._drop_args(6, "D", masks))
+        ops.bce_fwd_bwd(logit, 0.0, n_total, L[4:5], dz1)
+        D.backward(dz1, train=True)
+        D.apply_rmsprop()
+
+        # (7) generated_encodings = trainings_encoding_prediction(batch)     :138
+        genc = self.encode(x16, out32=self.gen_enc32[:B])
+        if self.variant == "classify":
+            ops.argmax_onehot(self.gen_enc32[:B], out16=self.gen_enc16[:B])
+            genc = self.gen_enc16[:B]
+
+        # (8) _discriminator.train_on_batch((generated_encodings, batch), y_ones)    :139
+        logit = D.forward({"z": genc, "cell": x16}, B, bn_train=True, pre_activation=True,
+                          **self._drop_args(8, "D", masks))
+        ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[5:6], dz1)
+        D.backward(dz1, train=True)
+        D.apply_rmsprop()
+
+        if masks is None:
+            ops.counter_add(self.rng_counter, 1)
+        self.dist.all_reduce(L)
+        Lc = L.clone()
+        g = LossScalar(Lc[0] + Lc[1])
+        e = LossScalar(Lc[2] + Lc[3])
+        d = LossScalar((Lc[4] + Lc[5]) * 0.5)       # np.mean([d_loss_1, d_loss_2])    :140
+        self.last_losses = Lc
+        return g, e, d
+
+    # ------------------------------------------------------------------ inference
+    def encode(self, x16, out32=None):
+        """E.predict on a [rows, gene_size] bf16 tile; fp32 result in out32 when given."""
+        return self.E.forward({"cell": x16}, x16.shape[0], bn_train=False, dropout="off",
+                              out32=out32)
+
+    def generate(self, rows, out32=None):
+        """G.predict on the staged latents (first `rows`)."""
+        return self.G.forward({"z": self.z16[:rows], "r": self.r16[:rows]}, rows, bn_train=False,
+                              dropout="off", out32=out32)
+
+    def discriminate(self, z16, x16, out32):
+        """D.predict -> probabilities (fp32 [rows,1])."""
+        return self.D.forward({"z": z16, "cell": x16}, x16.shape[0], bn_train=False, dropout="off",
+                              out32=out32)

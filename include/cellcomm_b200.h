@@ -1,0 +1,275 @@
+/*
+ * cellcomm_b200.h — C ABI of libcellcomm_b200.so
+ *
+ * The reference (mikemey/cellcomm) has no FFI/plugin interface: its hot path is
+ * Python calling tensorflow==2.4.0 Keras (requirements.txt:3).  This header is
+ * the boundary this repo introduces *underneath* the unchanged Python surface
+ * (SURVEY.md §8b): each entry point names the reference call it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.
+ *  - every call returns int: 0 = ok, <0 = error; cc_last_error() gives the text
+ *    (thread-local).
+ *  - device pointers are owned by the caller (torch's allocator in this repo).
+ *    The library allocates only inside opaque handles with an explicit
+ *    *_destroy, and inside host-side cc_coo/cc_csr objects.
+ *  - every device call is asynchronous on the cudaStream_t passed (as void*),
+ *    never synchronises, and is CUDA-graph capturable.
+ *  - 2-D device tensors are row-major with an explicit leading dimension `ld`
+ *    in ELEMENTS; bf16 tensors consumed by cc_gemm need ld % 8 == 0 and a
+ *    16-byte aligned base (TMA constraint).
+ */
+#ifndef CELLCOMM_B200_H
+#define CELLCOMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cc_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ misc */
+const char* cc_last_error(void);
+int cc_version(void);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim) */
+long long cc_launch_count(void);
+/* compiled-for architecture string, e.g. "sm_100a" */
+const char* cc_arch(void);
+
+/* ------------------------------------------------- loader (host, no GPU)
+ * replaces: load_matrix()  src/cell_type_training.py:9-17
+ *   pd.read_csv(skiprows=3, delim_whitespace=True, names=[gene,barcode,p])
+ *   .pivot_table(index=barcode, columns=gene, values=p, fill_value=0)
+ * Semantics: skip exactly 3 lines, ignore the dims line,
+ * rows = distinct barcode ids ascending, cols = distinct gene ids ascending,
+ * duplicate (gene,barcode) entries averaged in float64, explicit zeros keep
+ * their row/column alive.
+ */
+typedef struct cc_csr cc_csr; /* opaque host CSR */
+
+int cc_mtx_load_csr(const char* path, cc_csr** out);
+/* build the same CSR from in-memory COO triplets (1-based ids as in the file) */
+int cc_coo_to_csr(const int64_t* gene, const int64_t* barcode, const double* val,
+                  int64_t nnz, cc_csr** out);
+void cc_csr_destroy(cc_csr* csr);
+int64_t cc_csr_rows(const cc_csr* csr);
+int64_t cc_csr_cols(const cc_csr* csr);
+int64_t cc_csr_nnz(const cc_csr* csr);
+/* host views, valid until cc_csr_destroy */
+const int64_t* cc_csr_rowptr(const cc_csr* csr);   /* rows+1 */
+const int32_t* cc_csr_colidx(const cc_csr* csr);   /* nnz, compact column index, ascending per row */
+const float* cc_csr_values(const cc_csr* csr);     /* nnz, float32(mean as float64) */
+const double* cc_csr_values64(const cc_csr* csr);  /* nnz, the float64 means (DataFrame dtype) */
+const int64_t* cc_csr_row_ids(const cc_csr* csr);  /* rows, original barcode ids */
+const int64_t* cc_csr_col_ids(const cc_csr* csr);  /* cols, original gene ids */
+
+/* --------------------------------------------------- batch gather (device)
+ * replaces: DataFrame.sample(B) dense row gather, src/cell_type_training.py:37-38,
+ * and the DataFrame -> float32 tensor feed of train_on_batch/predict.
+ * row_idx_dev != NULL: output row i is CSR row row_idx_dev[i] (sampled batch);
+ * row_idx_dev == NULL: output row i is CSR row row_start + i (encode-all pass).
+ * out16/out32 may each be NULL.  Rows are fully written (zeros where the CSR
+ * has no entry) for columns [0, ld).
+ */
+int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_dev, const float* values_dev,
+                   const int64_t* row_idx_dev, int64_t row_start, int64_t n_rows, int64_t n_cols,
+                   void* out16, int64_t ld16, float* out32, int64_t ld32, cc_stream_t stream);
+
+/* ------------------------------------------------------------- dense GEMM
+ * replaces: layers.Dense forward/backward inside Model.train_on_batch /
+ * Model.predict (src/bigan_classify.py:10-75,144-155; src/bigan_cont.py:7-41).
+ *
+ * D[M,N] = epilogue( sum_s A_s[M,K_s] * B_s[K_s,N] ), bf16 operands, fp32
+ * accumulation in tensor memory (tcgen05).  Up to 3 (A_s,B_s) segments
+ * accumulate into one tile: that is how Concatenate() is consumed without
+ * materialising it.
+ *
+ * a_mn_major = 0: A_s is stored [M, K_s] row-major (K contiguous)
+ *            = 1: A_s is stored [K_s, M] row-major (M contiguous)
+ * b_mn_major = 0: B_s is stored [N, K_s] row-major (K contiguous)
+ *            = 1: B_s is stored [K_s, N] row-major (N contiguous)
+ *
+ * epilogue, per element (r,c), v = acc:
+ *   v = alpha * v
+ *   if bias:   v += bias[c]
+ *   act:       0 none, 1 sigmoid, 2 relu
+ *   if dact:   v *= act'(y[r,c])   (1: y(1-y)  2: y>0)   y = dact_y (bf16)
+ *   if out32:  out32[r,c] = v + (beta32 ? out32[r,c] : 0)
+ *   if out16:  out16[r,c] = bf16(v + (beta16 ? out16[r,c] : 0))
+ */
+enum { CC_ACT_NONE = 0, CC_ACT_SIGMOID = 1, CC_ACT_RELU = 2 };
+
+typedef struct cc_gemm_desc {
+  int32_t M, N;
+  int32_t a_mn_major, b_mn_major;
+  int32_t nseg;
+  const void* a[3];
+  int64_t lda[3];
+  const void* b[3];
+  int64_t ldb[3];
+  int32_t k[3];
+  /* epilogue */
+  float alpha;
+  const float* bias;
+  int32_t act;
+  const void* dact_y;
+  int64_t ld_dact;
+  int32_t dact;
+  void* out16;
+  int64_t ld16;
+  int32_t beta16;
+  float* out32;
+  int64_t ld32;
+  int32_t beta32;
+  /* split-K scratch (fp32), may be NULL => no split-K */
+  float* workspace;
+  int64_t workspace_elems;
+  /* tuning / debug overrides, 0 = automatic */
+  int32_t force_splits;
+  int32_t force_bn;
+  int32_t reserved[6];
+} cc_gemm_desc;
+
+int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);
+/* how many fp32 workspace elements cc_gemm may want for this shape */
+int64_t cc_gemm_workspace_elems(int32_t M, int32_t N);
+
+/* Layer-level wrappers (Keras kernel layout W[in,out], row-major, bf16):
+ *   fwd  : Y[M,N]   = act(sum_s X_s[M,K_s] W[roff_s : roff_s+K_s, :] + b)
+ *   dgrad: dX[M,K]  = (sum_s dZ_s[M,N_s] W_s[roff_s : roff_s+K, :]^T) * act'(y)
+ *   wgrad: dW[K,N]  = X[M,K]^T dZ[M,N]       (fp32 out)
+ * They fill a cc_gemm_desc and call cc_gemm; see gemm_api.cu.
+ */
+int cc_dense_fwd(int32_t M, int32_t N, int32_t nseg, const void* const* x, const int64_t* ldx,
+                 const int32_t* k, const void* const* w, const int64_t* ldw, const float* bias,
+                 int32_t act, void* out16, int64_t ld16, float* out32, int64_t ld32,
+                 float* workspace, int64_t workspace_elems, cc_stream_t stream);
+int cc_dense_dgrad(int32_t M, int32_t K, int32_t nseg, const void* const* dz, const int64_t* lddz,
+                   const int32_t* n, const void* const* w, const int64_t* ldw, const void* dact_y,
+                   int64_t ld_dact, int32_t dact, float alpha, void* out16, int64_t ld16,
+                   int32_t beta16, float* workspace, int64_t workspace_elems, cc_stream_t stream);
+int cc_dense_wgrad(int32_t M, int32_t K, int32_t N, const void* x, int64_t ldx, const void* dz,
+                   int64_t lddz, float* dw, int64_t lddw, int32_t beta, cc_stream_t stream);
+
+/* --------------------------------------------------------- tail kernels
+ * All elementwise / reduction kernels below work on row-major [rows, cols]
+ * tensors with explicit ld.  bf16 unless stated.
+ */
+
+/* column sums of a bf16 matrix into fp32: db = sum_rows dZ   (Dense bias grad) */
+int cc_colsum(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* out, int32_t beta,
+              cc_stream_t stream);
+
+/* Dropout (layers.Dropout, training=True): out = x * keep / (1-rate).
+ * mask_u8 != NULL: explicit keep mask (parity tests inject TF's masks this way).
+ * mask_u8 == NULL: keep = philox(seed, *counter_dev, stream_id, r, c) >= rate;
+ * the same call with the same arguments regenerates the mask in backward. */
+int cc_dropout(const void* x16, int64_t ldx, void* out16, int64_t ldo, int64_t rows, int64_t cols,
+               float rate, const uint8_t* mask_u8, int64_t ldm, uint64_t seed,
+               const uint64_t* counter_dev, uint32_t stream_id, cc_stream_t stream);
+/* write the keep mask the RNG path would use (tests / debugging) */
+int cc_dropout_mask(uint8_t* mask_u8, int64_t ldm, int64_t rows, int64_t cols, float rate,
+                    uint64_t seed, const uint64_t* counter_dev, uint32_t stream_id,
+                    cc_stream_t stream);
+/* uniform [0,1) floats: tf.random.uniform (src/bigan_basic.py:36-37, bigan_cont.py:52-53) */
+int cc_uniform(float* out32, void* out16, int64_t ld, int64_t rows, int64_t cols, uint64_t seed,
+               const uint64_t* counter_dev, uint32_t stream_id, cc_stream_t stream);
+int cc_counter_add(uint64_t* counter_dev, uint64_t inc, cc_stream_t stream);
+
+/* dz = dy * act'(y)  (act: 1 sigmoid, 2 relu), optional accumulate is not needed */
+int cc_act_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy, void* dz16,
+               int64_t lddz, int64_t rows, int64_t cols, int32_t act, cc_stream_t stream);
+
+/* copy a [rows, cols] block (concat materialisation / slicing); beta=1 accumulates */
+int cc_copy2d(const void* src16, int64_t lds, void* dst16, int64_t ldd, int64_t rows,
+              int64_t cols, int32_t beta, cc_stream_t stream);
+int cc_cast_f32_to_bf16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows,
+                        int64_t cols, cc_stream_t stream);
+int cc_cast_bf16_to_f32(const void* src16, int64_t lds, float* dst, int64_t ldd, int64_t rows,
+                        int64_t cols, float scale, cc_stream_t stream);
+
+/* BatchNormalization (Keras 2.4 defaults: eps=1e-3, momentum=0.99), SURVEY A.3.
+ * stats: sums[0:cols] = sum_r x, sums[cols:2cols] = sum_r x^2 (fp32, overwritten).
+ * The caller may all-reduce `sums` across ranks before cc_bn_train_apply. */
+int cc_bn_stats(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* sums,
+                cc_stream_t stream);
+/* y = gamma*(x-mean)*rstd+beta with batch stats from sums/n_total; writes
+ * mean/rstd (fp32, cols each) for backward; updates moving stats:
+ * moving = momentum*moving + (1-momentum)*batch (biased variance). */
+int cc_bn_train_apply(const void* x16, int64_t ldx, void* y16, int64_t ldy, int64_t rows,
+                      int64_t cols, const float* sums, int64_t n_total, const float* gamma,
+                      const float* beta, float eps, float momentum, float* moving_mean,
+                      float* moving_var, float* save_mean, float* save_rstd, cc_stream_t stream);
+/* inference: y = gamma*(x-moving_mean)/sqrt(moving_var+eps)+beta */
+int cc_bn_infer(const void* x16, int64_t ldx, void* y16, int64_t ldy, int64_t rows, int64_t cols,
+                const float* gamma, const float* beta, const float* moving_mean,
+                const float* moving_var, float eps, cc_stream_t stream);
+/* backward, training mode.  sums2[0:cols] = sum dy, sums2[cols:2cols] = sum dy*xhat */
+int cc_bn_bwd_stats(const void* dy16, int64_t lddy, const void* x16, int64_t ldx, int64_t rows,
+                    int64_t cols, const float* save_mean, const float* save_rstd, float* sums2,
+                    cc_stream_t stream);
+/* dx = gamma*rstd*(dy - sum_dy/n - xhat*sum_dyxhat/n); dgamma = sum_dyxhat, dbeta = sum_dy
+ * (dgamma/dbeta may be NULL when the BN is not being trained) */
+int cc_bn_bwd_apply(const void* dy16, int64_t lddy, const void* x16, int64_t ldx, void* dx16,
+                    int64_t lddx, int64_t rows, int64_t cols, const float* gamma,
+                    const float* save_mean, const float* save_rstd, const float* sums2,
+                    int64_t n_total, float* dgamma, float* dbeta, cc_stream_t stream);
+/* backward through an inference-mode (frozen) BN: dx = dy*gamma/sqrt(var+eps) */
+int cc_bn_infer_bwd(const void* dy16, int64_t lddy, void* dx16, int64_t lddx, int64_t rows,
+                    int64_t cols, const float* gamma, const float* moving_var, float eps,
+                    cc_stream_t stream);
+
+/* softmax over the last axis (classify encoder, src/bigan_classify.py:39) */
+int cc_softmax_fwd(const void* x16, int64_t ldx, void* y16, int64_t ldy, float* y32, int64_t ldy32,
+                   int64_t rows, int64_t cols, cc_stream_t stream);
+int cc_softmax_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy, void* dx16,
+                   int64_t lddx, int64_t rows, int64_t cols, cc_stream_t stream);
+
+/* losses.binary_crossentropy on the (rows,1) discriminator output against a
+ * constant target (0.95 / 0: src/bigan_classify.py:128-129).  Keras 2.4 uses the
+ * logits of the producing Sigmoid op (sigmoid_cross_entropy_with_logits), so the
+ * input is the PRE-activation (from_logits=1); from_logits=0 takes probabilities
+ * and clips them to [1e-7, 1-1e-7] (Keras backend epsilon).
+ * loss_out[0] += sum_r bce_r / n_total;  dz = dLoss/dlogit = (sigmoid(x)-t)/n_total
+ * (bf16, may be NULL).  n_total is the GLOBAL batch so sharded batches sum to the
+ * global mean. */
+int cc_bce_fwd_bwd(const float* x32, int64_t ldx, int64_t rows, int32_t from_logits, float target,
+                   int64_t n_total, float* loss_out, void* dz16, int64_t lddz, cc_stream_t stream);
+/* losses.mse: mean over all rows*cols elements; dpred = 2*(pred-target)/(n_total*cols) */
+int cc_mse_fwd_bwd(const void* pred16, int64_t ldp, const void* target16, int64_t ldt,
+                   const float* target32, int64_t ldt32, int64_t rows, int64_t cols,
+                   int64_t n_total, float* loss_out, void* dpred16, int64_t lddp,
+                   cc_stream_t stream);
+
+/* tf.math.round (half to even) for generate_cells, src/bigan_basic.py:40-44 */
+int cc_round_half_even(const void* x16, int64_t ldx, void* out16, int64_t ldo, float* out32,
+                       int64_t ldo32, int64_t rows, int64_t cols, cc_stream_t stream);
+/* to_categorical(argmax(p,-1)): src/bigan_classify.py:121-124 */
+int cc_argmax_onehot(const float* p32, int64_t ldp, void* out16, int64_t ldo, float* out32,
+                     int64_t ldo32, int64_t rows, int64_t cols, cc_stream_t stream);
+
+/* Keras RMSprop with momentum (optimizers.RMSprop(lr=0.0075, rho=0.85,
+ * momentum=0.1), src/bigan_classify.py:88):
+ *   ms  = rho*ms + (1-rho)*g^2 ; mom = momentum*mom + lr*g/sqrt(ms+eps) ; w -= mom
+ * Works on a [rows, cols] view with leading dimensions so that padded weight
+ * matrices can be updated in place; p16 (bf16 compute copy) may be NULL. */
+int cc_rmsprop_step(float* p32, void* p16, const float* g, float* ms, float* mom, int64_t rows,
+                    int64_t cols, int64_t ld, float lr, float rho, float momentum, float eps,
+                    float grad_scale, cc_stream_t stream);
+
+/* Dense layer with zero input width: y[r,c] = act(bias[c]).  The reference's 5-gene fixture
+ * produces Dense(0) layers (int(5*0.1) == 0; src/bigan_cont.py:8,29) whose consumers see K=0. */
+int cc_bias_act(const float* bias, int32_t act, void* out16, int64_t ld16, float* out32,
+                int64_t ld32, int64_t rows, int64_t cols, cc_stream_t stream);
+
+/* fp32 scalar helpers */
+int cc_fill_f32(float* dst, float value, int64_t n, cc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CELLCOMM_B200_H */

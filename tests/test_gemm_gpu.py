@@ -1,0 +1,199 @@
+"""tcgen05 GEMM (cc_gemm through the C ABI) against a plain PyTorch fp32 reference.
+
+Floating-point kernel => torch fp32 reference of the same op on the same bf16-rounded inputs.
+Tolerance: fp32 accumulation of bf16 products, so |err| <= 2e-3 * sqrt(K) * scale for fp32
+outputs, plus one bf16 rounding (rel 2^-8) for bf16 outputs.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from cellcomm_b200 import ops
+    return ops
+
+
+def _rand(rows, cols, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = (torch.randn(rows, cols, generator=g) * scale).to(torch.bfloat16)
+    return t
+
+
+def _dev2d(t_cpu, ops):
+    """copy into a padded device buffer, return the [rows, cols] view"""
+    out = ops.alloc2d(t_cpu.shape[0], t_cpu.shape[1], dtype=t_cpu.dtype)
+    out.copy_(t_cpu)
+    return out
+
+
+def _check(got, ref, K, bf16_out, scale=1.0):
+    got = got.float().cpu()
+    ref = ref.float().cpu()
+    atol = 2e-3 * (K ** 0.5) * scale + 1e-5
+    rtol = 2 ** -7 if bf16_out else 1e-4
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = (err > bound).sum().item()
+    assert bad == 0, (f"{bad} / {err.numel()} elements off; max err {err.max().item():.4g} "
+                      f"max ref {ref.abs().max().item():.4g}")
+
+
+SHAPES = [
+    (128, 128, 64),
+    (128, 256, 128),
+    (256, 384, 512),
+    (200, 300, 1000),
+    (77, 50, 33),
+    (3, 1, 10),
+    (130, 1684, 3369),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("bn", [128, 256])
+def test_dgrad_orientation_k_major(M, N, K, bn):
+    """A [M,K] K-major, B [N,K] K-major (dX = dZ W^T)."""
+    ops = _ops()
+    a, b = _rand(M, K, 1), _rand(N, K, 2)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 0, 0, out32=out, bn=bn)
+    torch.cuda.synchronize()
+    _check(out, a.float() @ b.float().t(), K, False)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("bn", [128, 256])
+def test_fwd_orientation_b_mn_major(M, N, K, bn):
+    """A [M,K] K-major, B [K,N] MN-major (Y = X W)."""
+    ops = _ops()
+    a, b = _rand(M, K, 3), _rand(K, N, 4)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 0, 1, out32=out, bn=bn)
+    torch.cuda.synchronize()
+    _check(out, a.float() @ b.float(), K, False)
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("bn", [128, 256])
+def test_wgrad_orientation_both_mn_major(M, N, K, bn):
+    """A stored [K,M], B stored [K,N] (dW = X^T dZ)."""
+    ops = _ops()
+    a, b = _rand(K, M, 5), _rand(K, N, 6)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 1, 1, out32=out, bn=bn)
+    torch.cuda.synchronize()
+    _check(out, a.float().t() @ b.float(), K, False)
+
+
+def test_a_mn_b_k_major():
+    ops = _ops()
+    M, N, K = 192, 160, 200
+    a, b = _rand(K, M, 7), _rand(N, K, 8)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 1, 0, out32=out)
+    torch.cuda.synchronize()
+    _check(out, a.float().t() @ b.float().t(), K, False)
+
+
+@pytest.mark.parametrize("splits", [2, 3, 7])
+def test_split_k(splits):
+    ops = _ops()
+    M, N, K = 128, 300, 4000
+    a, b = _rand(M, K, 9), _rand(K, N, 10)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    bias = torch.randn(N, device="cuda")
+    out16 = ops.alloc2d(M, N)
+    out32 = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 0, 1, bias=bias, act=ops.ACT_RELU, out16=out16, out32=out32,
+             splits=splits)
+    torch.cuda.synchronize()
+    ref = torch.relu(a.float() @ b.float() + bias.cpu())
+    _check(out32, ref, K, False)
+    _check(out16, ref, K, True)
+
+
+def test_auto_split_k_small_m_long_k():
+    ops = _ops()
+    M, N, K = 128, 512, 33694
+    a, b = _rand(M, K, 11, 0.1), _rand(K, N, 12, 0.1)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out32 = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], 0, 1, out32=out32)
+    torch.cuda.synchronize()
+    _check(out32, a.float() @ b.float(), K, False, scale=0.01)
+
+
+def test_concat_segments_forward():
+    """[h1, x] @ W without materialising the concat (E2/Dx2 in the reference nets)."""
+    ops = _ops()
+    M, N = 150, 200
+    ks = [100, 333, 6]
+    xs = [_rand(M, k, 20 + i) for i, k in enumerate(ks)]
+    w = _rand(sum(ks), N, 30)
+    dxs = [_dev2d(x, ops) for x in xs]
+    dw = _dev2d(w, ops)
+    bias = torch.randn(N, device="cuda")
+    out16 = ops.alloc2d(M, N)
+    ops.dense_fwd(dxs, dw, [0, 100, 433], bias, ops.ACT_SIGMOID, out16=out16)
+    torch.cuda.synchronize()
+    ref = torch.sigmoid(torch.cat([x.float() for x in xs], 1) @ w.float() + bias.cpu())
+    _check(out16, ref, sum(ks), True)
+
+
+def test_dgrad_with_act_derivative_and_accumulate():
+    ops = _ops()
+    M, K, N = 140, 260, 90
+    dz, w = _rand(M, N, 40), _rand(K, N, 41)
+    y = torch.sigmoid(_rand(M, K, 42).float()).to(torch.bfloat16)
+    prev = _rand(M, K, 43)
+    ddz, dw, dy = _dev2d(dz, ops), _dev2d(w, ops), _dev2d(y, ops)
+    out = _dev2d(prev, ops)
+    ops.dense_dgrad([ddz], [dw], out, dact_y=dy, dact=ops.ACT_SIGMOID, alpha=0.5, beta=1)
+    torch.cuda.synchronize()
+    ref = prev.float() + 0.5 * (dz.float() @ w.float().t()) * (y.float() * (1 - y.float()))
+    _check(out, ref, N, True)
+
+
+def test_dgrad_two_segments():
+    """d(cell) = dZ1 W1^T + dZ2 W2x^T (sub-step 1 of trainings_step through D's skip concat)."""
+    ops = _ops()
+    M, K = 100, 500
+    n1, n2 = 300, 120
+    dz1, dz2 = _rand(M, n1, 50), _rand(M, n2, 51)
+    w1, w2 = _rand(K, n1, 52), _rand(K + 40, n2, 53)
+    out = ops.alloc2d(M, K)
+    dw2 = _dev2d(w2, ops)
+    ops.dense_dgrad([_dev2d(dz1, ops), _dev2d(dz2, ops)], [_dev2d(w1, ops), dw2[40:]], out)
+    torch.cuda.synchronize()
+    ref = dz1.float() @ w1.float().t() + dz2.float() @ w2[40:].float().t()
+    _check(out, ref, n1 + n2, True)
+
+
+def test_wgrad_into_row_block_and_beta():
+    ops = _ops()
+    B, K, N = 128, 200, 170
+    x, dz = _rand(B, K, 60), _rand(B, N, 61)
+    dw = ops.alloc2d(K + 30, N, dtype=torch.float32)
+    dw.fill_(1.0)
+    ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), dw[30:], beta=1)
+    torch.cuda.synchronize()
+    ref = 1.0 + x.float().t() @ dz.float()
+    _check(dw[30:], ref, B, False)
+    assert torch.all(dw[:30] == 1.0)
+
+
+def test_large_batch_shapes():
+    ops = _ops()
+    M, N, K = 1024, 1024, 2048
+    a, b = _rand(M, K, 70), _rand(K, N, 71)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out16 = ops.alloc2d(M, N)
+    ops.gemm(M, N, [da], [db], [K], 0, 1, out16=out16)
+    torch.cuda.synchronize()
+    _check(out16, a.float() @ b.float(), K, True)
