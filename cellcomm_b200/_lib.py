@@ -19,9 +19,9 @@ class GemmDesc(C.Structure):
         ("M", c_i32), ("N", c_i32),
         ("a_mn_major", c_i32), ("b_mn_major", c_i32),
         ("nseg", c_i32),
-        ("a", vp * 3), ("lda", c_i64 * 3),
-        ("b", vp * 3), ("ldb", c_i64 * 3),
-        ("k", c_i32 * 3),
+        ("a", vp * 4), ("lda", c_i64 * 4),
+        ("b", vp * 4), ("ldb", c_i64 * 4),
+        ("k", c_i32 * 4),
         ("alpha", c_f32),
         ("bias", vp), ("act", c_i32),
         ("dact_y", vp), ("ld_dact", c_i64), ("dact", c_i32),
@@ -61,30 +61,31 @@ SIGNATURES = {
                                  C.POINTER(c_i32), C.POINTER(vp), C.POINTER(c_i64), vp, c_i64,
                                  c_i32, c_f32, vp, c_i64, c_i32, vp, c_i64, vp]),
     "cc_dense_wgrad": (C.c_int, [c_i32, c_i32, c_i32, vp, c_i64, vp, c_i64, vp, c_i64, c_i32, vp]),
-    "cc_colsum": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, vp]),
+    "cc_colsum": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, c_i32, vp]),
+    "cc_bias_grad": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp, c_i32, vp]),
+    "cc_split_bf16": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
     "cc_dropout": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp, c_i64, c_u64, vp,
-                             c_u32, vp]),
+                             c_u32, c_i32, vp]),
     "cc_dropout_mask": (C.c_int, [vp, c_i64, c_i64, c_i64, c_f32, c_u64, vp, c_u32, vp]),
     "cc_uniform": (C.c_int, [vp, vp, c_i64, c_i64, c_i64, c_u64, vp, c_u32, vp]),
     "cc_counter_add": (C.c_int, [vp, c_u64, vp]),
-    "cc_act_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
-    "cc_copy2d": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
-    "cc_cast_f32_to_bf16": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
-    "cc_cast_bf16_to_f32": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp]),
-    "cc_bn_stats": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, vp]),
+    "cc_act_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, c_i32, vp]),
+    "cc_copy2d": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, c_f32, c_i32, vp]),
+    "cc_bn_stats": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, vp]),
     "cc_bn_train_apply": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, c_i64, vp, vp, c_f32,
-                                    c_f32, vp, vp, vp, vp, vp]),
-    "cc_bn_infer": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp, c_f32, vp]),
-    "cc_bn_bwd_stats": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp]),
+                                    c_f32, vp, vp, vp, vp, c_i32, vp]),
+    "cc_bn_infer": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp, c_f32, c_i32,
+                              vp]),
+    "cc_bn_bwd_stats": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, c_i32, vp]),
     "cc_bn_bwd_apply": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, vp, vp,
-                                  c_i64, vp, vp, vp]),
-    "cc_bn_infer_bwd": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, c_f32, vp]),
-    "cc_softmax_fwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
-    "cc_softmax_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
-    "cc_bce_fwd_bwd": (C.c_int, [vp, c_i64, c_i64, c_i32, c_f32, c_i64, vp, vp, c_i64, vp]),
-    "cc_mse_fwd_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i64, vp, vp,
-                                 c_i64, vp]),
-    "cc_round_half_even": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
+                                  c_i64, vp, vp, c_i32, vp]),
+    "cc_bn_infer_bwd": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, vp, vp, c_f32, c_i32, vp]),
+    "cc_softmax_fwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
+    "cc_softmax_bwd": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
+    "cc_bce_fwd_bwd": (C.c_int, [vp, c_i64, c_i64, c_i32, c_f32, c_i64, vp, vp, c_i64, c_i32, vp]),
+    "cc_mse_fwd_bwd": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i64, vp, vp, c_i64, c_i32,
+                                 vp]),
+    "cc_round_half_even": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
     "cc_argmax_onehot": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
     "cc_rmsprop_step": (C.c_int, [vp, vp, vp, vp, vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
                                   c_f32, c_f32, vp]),

@@ -16,7 +16,7 @@ extern "C" int cc_dense_fwd(int32_t M, int32_t N, int32_t nseg, const void* cons
                             const int64_t* ldw, const float* bias, int32_t act, void* out16,
                             int64_t ld16, float* out32, int64_t ld32, float* workspace,
                             int64_t workspace_elems, cc_stream_t stream) {
-  CC_REQUIRE(nseg >= 1 && nseg <= 3, "cc_dense_fwd: nseg=%d", nseg);
+  CC_REQUIRE(nseg >= 1 && nseg <= CC_GEMM_MAX_SEG, "cc_dense_fwd: nseg=%d", nseg);
   cc_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M;
@@ -48,7 +48,7 @@ extern "C" int cc_dense_dgrad(int32_t M, int32_t K, int32_t nseg, const void* co
                               const int64_t* ldw, const void* dact_y, int64_t ld_dact,
                               int32_t dact, float alpha, void* out16, int64_t ld16, int32_t beta16,
                               float* workspace, int64_t workspace_elems, cc_stream_t stream) {
-  CC_REQUIRE(nseg >= 1 && nseg <= 3, "cc_dense_dgrad: nseg=%d", nseg);
+  CC_REQUIRE(nseg >= 1 && nseg <= CC_GEMM_MAX_SEG, "cc_dense_dgrad: nseg=%d", nseg);
   cc_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M;

@@ -28,7 +28,7 @@ namespace cc {
 constexpr int BM = 128;     // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 64;      // k-block: 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;  // fixed for 16-bit inputs
-constexpr int MAX_SEG = 3;
+constexpr int MAX_SEG = CC_GEMM_MAX_SEG;
 
 struct EpiParams {
   int M, N;

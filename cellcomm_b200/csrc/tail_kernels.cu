@@ -34,34 +34,79 @@ struct alignas(16) bf16x8 {
   __nv_bfloat162 v[4];
 };
 
-__device__ __forceinline__ void load8(const bf16* p, bool vec, int n, float (&f)[8]) {
-  if (vec && n == 8) {
-    bf16x8 q = *reinterpret_cast<const bf16x8*>(p);
+// A row-major [rows, cols] operand that is either bf16 or fp32 (activations that feed a
+// BatchNormalization and all activation gradients are kept in fp32).
+struct Mat {
+  void* p;
+  long long ld;
+  int f32;
+};
+static inline Mat mat(const void* p, long long ld, int f32) {
+  return Mat{const_cast<void*>(p), ld, f32};
+}
+
+__device__ __forceinline__ void load8(const Mat& m, long long r, long long c0, int n,
+                                      float (&f)[8]) {
+  if (m.f32) {
+    const float* p = reinterpret_cast<const float*>(m.p) + r * m.ld + c0;
+    if (n == 8 && (m.ld % 4) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      const float4 a = *reinterpret_cast<const float4*>(p);
+      const float4 b = *reinterpret_cast<const float4*>(p + 4);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+      f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 t = __bfloat1622float2(q.v[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
+      for (int i = 0; i < 8; ++i) f[i] = (i < n) ? p[i] : 0.f;
     }
   } else {
+    const bf16* p = reinterpret_cast<const bf16*>(m.p) + r * m.ld + c0;
+    if (n == 8 && (m.ld % 8) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      bf16x8 q = *reinterpret_cast<const bf16x8*>(p);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = (i < n) ? bf2f(p[i]) : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(q.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = (i < n) ? bf2f(p[i]) : 0.f;
+    }
   }
 }
-__device__ __forceinline__ void store8(bf16* p, bool vec, int n, const float (&f)[8]) {
-  if (vec && n == 8) {
-    bf16x8 q;
+__device__ __forceinline__ void store8(const Mat& m, long long r, long long c0, int n,
+                                       const float (&f)[8]) {
+  if (m.f32) {
+    float* p = reinterpret_cast<float*>(m.p) + r * m.ld + c0;
+    if (n == 8 && (m.ld % 4) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) q.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-    *reinterpret_cast<bf16x8*>(p) = q;
+      for (int i = 0; i < 8; ++i)
+        if (i < n) p[i] = f[i];
+    }
   } else {
+    bf16* p = reinterpret_cast<bf16*>(m.p) + r * m.ld + c0;
+    if (n == 8 && (m.ld % 8) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      bf16x8 q;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < n) p[i] = f2bf(f[i]);
+      for (int i = 0; i < 4; ++i) q.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      *reinterpret_cast<bf16x8*>(p) = q;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < n) p[i] = f2bf(f[i]);
+    }
   }
 }
-__host__ __device__ inline bool vec_ok(const void* p, long long ld) {
-  return (((uintptr_t)p) & 15) == 0 && (ld % 8) == 0;
+__device__ __forceinline__ float load1(const Mat& m, long long r, long long c) {
+  return m.f32 ? reinterpret_cast<const float*>(m.p)[r * m.ld + c]
+               : bf2f(reinterpret_cast<const bf16*>(m.p)[r * m.ld + c]);
+}
+__device__ __forceinline__ void store1(const Mat& m, long long r, long long c, float v) {
+  if (m.f32) reinterpret_cast<float*>(m.p)[r * m.ld + c] = v;
+  else reinterpret_cast<bf16*>(m.p)[r * m.ld + c] = f2bf(v);
 }
 
 // Iterate over [rows, cols] in chunks of 8 consecutive columns; F(row, col0, nvalid).
@@ -94,16 +139,15 @@ __device__ __forceinline__ void rng8(uint64_t seed, uint64_t step, uint32_t stre
   for (int i = 0; i < 4; ++i) u[4 + i] = u32_to_unit(o[i]);
 }
 
-__global__ void dropout_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out,
-                               long long ldo, long long rows, long long cols, float rate,
-                               const uint8_t* __restrict__ mask, long long ldm, uint64_t seed,
-                               const uint64_t* __restrict__ counter, uint32_t stream_id) {
+__global__ void dropout_kernel(const Mat x, const Mat out, long long rows, long long cols,
+                               float rate, const uint8_t* __restrict__ mask, long long ldm,
+                               uint64_t seed, const uint64_t* __restrict__ counter,
+                               uint32_t stream_id) {
   const float scale = 1.f / (1.f - rate);
   const uint64_t step = counter ? *counter : 0;
-  const bool vx = vec_ok(x, ldx), vo = vec_ok(out, ldo);
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float f[8];
-    load8(x + r * ldx + c0, vx, n, f);
+    load8(x, r, c0, n, f);
     if (mask != nullptr) {
       const uint8_t* m = mask + r * ldm + c0;
 #pragma unroll
@@ -115,7 +159,7 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, long long ldx, bf16* 
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = (u[i] >= rate) ? f[i] * scale : 0.f;
     }
-    store8(out + r * ldo + c0, vo, n, f);
+    store8(out, r, c0, n, f);
   });
 }
 
@@ -147,71 +191,63 @@ __global__ void uniform_kernel(float* __restrict__ out32, bf16* __restrict__ out
 __global__ void counter_add_kernel(uint64_t* counter, uint64_t inc) { *counter += inc; }
 
 // ------------------------------------------------------------------ simple elementwise
-__global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long lddy,
-                               const bf16* __restrict__ y, long long ldy, bf16* __restrict__ dz,
-                               long long lddz, long long rows, long long cols, int act) {
-  const bool v1 = vec_ok(dy, lddy), v2 = vec_ok(y, ldy), v3 = vec_ok(dz, lddz);
+__global__ void act_bwd_kernel(const Mat dy, const Mat y, const Mat dz, long long rows,
+                               long long cols, int act) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float g[8], a[8];
-    load8(dy + r * lddy + c0, v1, n, g);
-    load8(y + r * ldy + c0, v2, n, a);
+    load8(dy, r, c0, n, g);
+    load8(y, r, c0, n, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       g[i] *= (act == CC_ACT_SIGMOID) ? a[i] * (1.f - a[i])
                                       : (act == CC_ACT_RELU ? (a[i] > 0.f ? 1.f : 0.f) : 1.f);
-    store8(dz + r * lddz + c0, v3, n, g);
+    store8(dz, r, c0, n, g);
   });
 }
 
-__global__ void copy2d_kernel(const bf16* __restrict__ src, long long lds, bf16* __restrict__ dst,
-                              long long ldd, long long rows, long long cols, int beta) {
-  const bool v1 = vec_ok(src, lds), v2 = vec_ok(dst, ldd);
+__global__ void copy2d_kernel(const Mat src, const Mat dst, long long rows, long long cols,
+                              int beta, float scale) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float f[8];
-    load8(src + r * lds + c0, v1, n, f);
+    load8(src, r, c0, n, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= scale;
     if (beta) {
       float o[8];
-      load8(dst + r * ldd + c0, v2, n, o);
+      load8(dst, r, c0, n, o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] += o[i];
     }
-    store8(dst + r * ldd + c0, v2, n, f);
+    store8(dst, r, c0, n, f);
   });
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds,
-                                     bf16* __restrict__ dst, long long ldd, long long rows,
-                                     long long cols) {
-  const bool v2 = vec_ok(dst, ldd);
+// hi = bf16(x), lo = bf16(x - hi): a two-term bf16 expansion of an fp32 activation, consumed
+// as two accumulating GEMM segments where 8 mantissa bits are not enough (inputs of the Dense
+// layers that feed a BatchNormalization, see DESIGN.md "precision policy").
+__global__ void split_kernel(const Mat x, const Mat hi, const Mat lo, long long rows,
+                             long long cols) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
-    float f[8];
+    float f[8], h[8], l[8];
+    load8(x, r, c0, n, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = (i < n) ? src[r * lds + c0 + i] : 0.f;
-    store8(dst + r * ldd + c0, v2, n, f);
+    for (int i = 0; i < 8; ++i) {
+      h[i] = bf2f(f2bf(f[i]));
+      l[i] = f[i] - h[i];
+    }
+    store8(hi, r, c0, n, h);
+    store8(lo, r, c0, n, l);
   });
 }
 
-__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds,
-                                     float* __restrict__ dst, long long ldd, long long rows,
-                                     long long cols, float scale) {
-  const bool v1 = vec_ok(src, lds);
+__global__ void round_kernel(const Mat x, const Mat out, float* __restrict__ out32,
+                             long long ldo32, long long rows, long long cols) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float f[8];
-    load8(src + r * lds + c0, v1, n, f);
-    for (int i = 0; i < n; ++i) dst[r * ldd + c0 + i] = f[i] * scale;
-  });
-}
-
-__global__ void round_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out16,
-                             long long ldo, float* __restrict__ out32, long long ldo32,
-                             long long rows, long long cols) {
-  const bool v1 = vec_ok(x, ldx), v2 = out16 && vec_ok(out16, ldo);
-  for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
-    float f[8];
-    load8(x + r * ldx + c0, v1, n, f);
+    load8(x, r, c0, n, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = rintf(f[i]);  // round half to even (tf.math.round)
-    if (out16) store8(out16 + r * ldo + c0, v2, n, f);
+    if (out.p) store8(out, r, c0, n, f);
     if (out32)
       for (int i = 0; i < n; ++i) out32[r * ldo32 + c0 + i] = f[i];
   });
@@ -241,14 +277,38 @@ __global__ void fill_f32_kernel(float* dst, float v, long long n) {
 
 // ------------------------------------------------------------------ column reductions
 // out[c] = sum_r f0(r,c), out[cols + c] = sum_r f1(r,c).  A block of 32x8 threads owns 64
-// columns (one bf162 per thread per row) and strides over a slab of rows; slabs combine with
-// atomics only when there is more than one slab (grid.y > 1).
-template <int MODE>  // 0: x (1 output)  1: x, x^2   2: dy, dy*xhat
-__global__ void colreduce_kernel(const bf16* __restrict__ a, long long lda,
-                                 const bf16* __restrict__ b, long long ldb, long long rows,
-                                 long long cols, const float* __restrict__ mean,
-                                 const float* __restrict__ rstd, float* __restrict__ out,
-                                 int accumulate) {
+// columns (two adjacent columns per thread per row) and strides over a slab of rows; slabs
+// combine with atomics only when there is more than one slab (grid.y > 1).
+__device__ __forceinline__ void load_pair(const Mat& m, long long r, long long c, bool c0ok,
+                                          bool c1ok, float& x0, float& x1) {
+  x0 = x1 = 0.f;
+  if (m.f32) {
+    const float* p = reinterpret_cast<const float*>(m.p) + r * m.ld + c;
+    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
+      const float2 t = *reinterpret_cast<const float2*>(p);
+      x0 = t.x;
+      x1 = t.y;
+    } else {
+      if (c0ok) x0 = p[0];
+      if (c1ok) x1 = p[1];
+    }
+  } else {
+    const bf16* p = reinterpret_cast<const bf16*>(m.p) + r * m.ld + c;
+    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 3) == 0)) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+      x0 = t.x;
+      x1 = t.y;
+    } else {
+      if (c0ok) x0 = bf2f(p[0]);
+      if (c1ok) x1 = bf2f(p[1]);
+    }
+  }
+}
+
+template <int MODE>  // 0: x (1 output)  1: x, x^2   2: dy, dy*xhat   3: dy*act'(y) (1 output)
+__global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long long cols,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 float* __restrict__ out, int accumulate, int act) {
   __shared__ float s0[8][64], s1[8][64];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long c = (long long)blockIdx.x * 64 + tx * 2;
@@ -257,38 +317,36 @@ __global__ void colreduce_kernel(const bf16* __restrict__ a, long long lda,
   const long long r_end = min(rows, r_begin + rows_per_slab);
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
   const bool c0ok = c < cols, c1ok = c + 1 < cols;
-  const bool pair = c1ok && ((lda & 1) == 0) && ((((uintptr_t)a) & 3) == 0);
   float m0 = 0.f, m1 = 0.f, q0 = 0.f, q1 = 0.f;
   if (MODE == 2) {
     if (c0ok) { m0 = mean[c]; q0 = rstd[c]; }
     if (c1ok) { m1 = mean[c + 1]; q1 = rstd[c + 1]; }
   }
-  for (long long r = r_begin + ty; r < r_end; r += 8) {
-    float x0 = 0.f, x1 = 0.f;
-    if (pair) {
-      float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + r * lda + c));
-      x0 = t.x;
-      x1 = t.y;
-    } else {
-      if (c0ok) x0 = bf2f(a[r * lda + c]);
-      if (c1ok) x1 = bf2f(a[r * lda + c + 1]);
-    }
-    if (MODE == 0) {
-      a0 += x0;
-      a1 += x1;
-    } else if (MODE == 1) {
-      a0 += x0;
-      a1 += x1;
-      b0 += x0 * x0;
-      b1 += x1 * x1;
-    } else {
-      float y0 = 0.f, y1 = 0.f;
-      if (c0ok) y0 = bf2f(b[r * ldb + c]);
-      if (c1ok) y1 = bf2f(b[r * ldb + c + 1]);
-      a0 += x0;
-      a1 += x1;
-      b0 += x0 * ((y0 - m0) * q0);
-      b1 += x1 * ((y1 - m1) * q1);
+  if (c0ok) {
+    for (long long r = r_begin + ty; r < r_end; r += 8) {
+      float x0, x1;
+      load_pair(a, r, c, c0ok, c1ok, x0, x1);
+      if (MODE == 0) {
+        a0 += x0;
+        a1 += x1;
+      } else if (MODE == 1) {
+        a0 += x0;
+        a1 += x1;
+        b0 += x0 * x0;
+        b1 += x1 * x1;
+      } else if (MODE == 2) {
+        float y0, y1;
+        load_pair(b, r, c, c0ok, c1ok, y0, y1);
+        a0 += x0;
+        a1 += x1;
+        b0 += x0 * ((y0 - m0) * q0);
+        b1 += x1 * ((y1 - m1) * q1);
+      } else {
+        float y0 = 0.f, y1 = 0.f;
+        if (act != 0) load_pair(b, r, c, c0ok, c1ok, y0, y1);
+        a0 += x0 * (act == CC_ACT_SIGMOID ? y0 * (1.f - y0) : (act == CC_ACT_RELU ? (y0 > 0.f ? 1.f : 0.f) : 1.f));
+        a1 += x1 * (act == CC_ACT_SIGMOID ? y1 * (1.f - y1) : (act == CC_ACT_RELU ? (y1 > 0.f ? 1.f : 0.f) : 1.f));
+      }
     }
   }
   s0[ty][tx * 2] = a0;
@@ -310,19 +368,19 @@ __global__ void colreduce_kernel(const bf16* __restrict__ a, long long lda,
       }
       if (gridDim.y > 1 || accumulate) {
         atomicAdd(out + cc_, t0);
-        if (MODE != 0) atomicAdd(out + cols + cc_, t1);
+        if (MODE == 1 || MODE == 2) atomicAdd(out + cols + cc_, t1);
       } else {
         out[cc_] = t0;
-        if (MODE != 0) out[cols + cc_] = t1;
+        if (MODE == 1 || MODE == 2) out[cols + cc_] = t1;
       }
     }
   }
 }
 
 template <int MODE>
-static int launch_colreduce(const bf16* a, long long lda, const bf16* b, long long ldb,
-                            long long rows, long long cols, const float* mean, const float* rstd,
-                            float* out, int accumulate, cudaStream_t st) {
+static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long long cols,
+                            const float* mean, const float* rstd, float* out, int accumulate,
+                            cudaStream_t st, int act = 0) {
   const unsigned gx = (unsigned)((cols + 63) / 64);
   // enough row slabs to cover ~2 waves of the machine when there are few column blocks
   unsigned gy = 1;
@@ -334,12 +392,12 @@ static int launch_colreduce(const bf16* a, long long lda, const bf16* b, long lo
     if (gy < 1) gy = 1;
   }
   if (gy > 1 && !accumulate) {
-    const long long n = (MODE == 0 ? 1 : 2) * cols;
+    const long long n = ((MODE == 0 || MODE == 3) ? 1 : 2) * cols;
     fill_f32_kernel<<<ew_grid(n, 256), 256, 0, st>>>(out, 0.f, n);
     CC_CHECK_LAUNCH();
   }
-  colreduce_kernel<MODE><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(a, lda, b, ldb, rows, cols, mean,
-                                                               rstd, out, accumulate);
+  colreduce_kernel<MODE><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(a, b, rows, cols, mean, rstd, out,
+                                                               accumulate, act);
   CC_CHECK_LAUNCH();
   return 0;
 }
@@ -353,9 +411,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long col
                                    float* __restrict__ save_rstd) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  const float mean = (float)(sums[c] * inv_n);
-  float var = (float)(sums[cols + c] * inv_n) - mean * mean;
-  var = fmaxf(var, 0.f);
+  const double mean_d = (double)sums[c] * inv_n;
+  double var_d = (double)sums[cols + c] * inv_n - mean_d * mean_d;
+  const float mean = (float)mean_d;
+  const float var = fmaxf((float)var_d, 0.f);
   save_mean[c] = mean;
   save_rstd[c] = rsqrtf(var + eps);
   if (moving_mean) moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
@@ -364,15 +423,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long col
 
 // y = (x - mean) * (gamma * rstd) + beta ; (mean, rstd) either saved batch stats or derived
 // from moving stats (infer != 0: rstd := 1/sqrt(var+eps))
-__global__ void bn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y,
-                                long long ldy, long long rows, long long cols,
+__global__ void bn_apply_kernel(const Mat x, const Mat y, long long rows, long long cols,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ mean, const float* __restrict__ stat,
                                 int infer, float eps) {
-  const bool v1 = vec_ok(x, ldx), v2 = vec_ok(y, ldy);
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float f[8];
-    load8(x + r * ldx + c0, v1, n, f);
+    load8(x, r, c0, n, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < n) {
@@ -381,22 +438,19 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
         f[i] = (f[i] - mean[c]) * (gamma[c] * rs) + beta[c];
       }
     }
-    store8(y + r * ldy + c0, v2, n, f);
+    store8(y, r, c0, n, f);
   });
 }
 
 // dx = gamma*rstd*(dy - sum_dy/n - xhat*sum_dyxhat/n)
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
-                                    const bf16* __restrict__ x, long long ldx,
-                                    bf16* __restrict__ dx, long long lddx, long long rows,
+__global__ void bn_bwd_apply_kernel(const Mat dy, const Mat x, const Mat dx, long long rows,
                                     long long cols, const float* __restrict__ gamma,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ sums2, float inv_n) {
-  const bool v1 = vec_ok(dy, lddy), v2 = vec_ok(x, ldx), v3 = vec_ok(dx, lddx);
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float g[8], a[8];
-    load8(dy + r * lddy + c0, v1, n, g);
-    load8(x + r * ldx + c0, v2, n, a);
+    load8(dy, r, c0, n, g);
+    load8(x, r, c0, n, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < n) {
@@ -405,7 +459,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long lddy,
         g[i] = gamma[c] * rstd[c] * (g[i] - sums2[c] * inv_n - xhat * sums2[cols + c] * inv_n);
       }
     }
-    store8(dx + r * lddx + c0, v3, n, g);
+    store8(dx, r, c0, n, g);
   });
 }
 
@@ -417,51 +471,44 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ sums2, long long 
   if (dgamma) dgamma[c] = sums2[cols + c];
 }
 
-__global__ void bn_infer_bwd_kernel(const bf16* __restrict__ dy, long long lddy,
-                                    bf16* __restrict__ dx, long long lddx, long long rows,
-                                    long long cols, const float* __restrict__ gamma,
+__global__ void bn_infer_bwd_kernel(const Mat dy, const Mat dx, long long rows, long long cols,
+                                    const float* __restrict__ gamma,
                                     const float* __restrict__ var, float eps) {
-  const bool v1 = vec_ok(dy, lddy), v3 = vec_ok(dx, lddx);
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float g[8];
-    load8(dy + r * lddy + c0, v1, n, g);
+    load8(dy, r, c0, n, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i < n) g[i] *= gamma[c0 + i] * rsqrtf(var[c0 + i] + eps);
-    store8(dx + r * lddx + c0, v3, n, g);
+    store8(dx, r, c0, n, g);
   });
 }
 
 // ------------------------------------------------------------------ softmax / one-hot
-__global__ void softmax_fwd_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y,
-                                   long long ldy, float* __restrict__ y32, long long ldy32,
-                                   long long rows, long long cols) {
+__global__ void softmax_fwd_kernel(const Mat x, const Mat y, float* __restrict__ y32,
+                                   long long ldy32, long long rows, long long cols) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float mx = -INFINITY;
-  for (long long c = 0; c < cols; ++c) mx = fmaxf(mx, bf2f(x[r * ldx + c]));
+  for (long long c = 0; c < cols; ++c) mx = fmaxf(mx, load1(x, r, c));
   float sum = 0.f;
-  for (long long c = 0; c < cols; ++c) sum += __expf(bf2f(x[r * ldx + c]) - mx);
+  for (long long c = 0; c < cols; ++c) sum += __expf(load1(x, r, c) - mx);
   const float inv = 1.f / sum;
   for (long long c = 0; c < cols; ++c) {
-    const float v = __expf(bf2f(x[r * ldx + c]) - mx) * inv;
-    if (y) y[r * ldy + c] = f2bf(v);
+    const float v = __expf(load1(x, r, c) - mx) * inv;
+    if (y.p) store1(y, r, c, v);
     if (y32) y32[r * ldy32 + c] = v;
   }
 }
 
-__global__ void softmax_bwd_kernel(const bf16* __restrict__ dy, long long lddy,
-                                   const bf16* __restrict__ y, long long ldy,
-                                   bf16* __restrict__ dx, long long lddx, long long rows,
+__global__ void softmax_bwd_kernel(const Mat dy, const Mat y, const Mat dx, long long rows,
                                    long long cols) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float dot = 0.f;
-  for (long long c = 0; c < cols; ++c) dot += bf2f(dy[r * lddy + c]) * bf2f(y[r * ldy + c]);
-  for (long long c = 0; c < cols; ++c) {
-    const float yy = bf2f(y[r * ldy + c]);
-    dx[r * lddx + c] = f2bf(yy * (bf2f(dy[r * lddy + c]) - dot));
-  }
+  for (long long c = 0; c < cols; ++c) dot += load1(dy, r, c) * load1(y, r, c);
+  for (long long c = 0; c < cols; ++c)
+    store1(dx, r, c, load1(y, r, c) * (load1(dy, r, c) - dot));
 }
 
 __global__ void argmax_onehot_kernel(const float* __restrict__ p, long long ldp,
@@ -507,7 +554,7 @@ __device__ __forceinline__ float block_sum(float v) {
 // Keras binary_crossentropy for a sigmoid output (logits form, see cellcomm_b200.h).
 __global__ void bce_kernel(const float* __restrict__ x, long long ldx, long long rows,
                            int from_logits, float target, float inv_n,
-                           float* __restrict__ loss_out, bf16* __restrict__ dz, long long lddz) {
+                           float* __restrict__ loss_out, const Mat dz) {
   float acc = 0.f;
   for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
     const float raw = x[r * ldx];
@@ -523,28 +570,19 @@ __global__ void bce_kernel(const float* __restrict__ x, long long ldx, long long
       loss = -(target * logf(q) + (1.f - target) * logf(1.f - q));
     }
     acc += loss;
-    if (dz) dz[r * lddz] = f2bf((p - target) * inv_n);
+    if (dz.p) store1(dz, r, 0, (p - target) * inv_n);
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(loss_out, acc * inv_n);
 }
 
-__global__ void mse_kernel(const bf16* __restrict__ pred, long long ldp,
-                           const bf16* __restrict__ t16, long long ldt,
-                           const float* __restrict__ t32, long long ldt32, long long rows,
-                           long long cols, float inv_total, float* __restrict__ loss_out,
-                           bf16* __restrict__ dpred, long long lddp) {
-  const bool v1 = vec_ok(pred, ldp), v2 = t16 && vec_ok(t16, ldt), v3 = dpred && vec_ok(dpred, lddp);
+__global__ void mse_kernel(const Mat pred, const Mat target, long long rows, long long cols,
+                           float inv_total, float* __restrict__ loss_out, const Mat dpred) {
   float acc = 0.f;
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
     float a[8], t[8];
-    load8(pred + r * ldp + c0, v1, n, a);
-    if (t16) {
-      load8(t16 + r * ldt + c0, v2, n, t);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = (i < n) ? t32[r * ldt32 + c0 + i] : 0.f;
-    }
+    load8(pred, r, c0, n, a);
+    load8(target, r, c0, n, t);
     float g[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -552,7 +590,7 @@ __global__ void mse_kernel(const bf16* __restrict__ pred, long long ldp,
       acc += d * d;
       g[i] = 2.f * d * inv_total;
     }
-    if (dpred) store8(dpred + r * lddp + c0, v3, n, g);
+    if (dpred.p) store8(dpred, r, c0, n, g);
   });
   acc = block_sum(acc);
   if (threadIdx.x == 0) atomicAdd(loss_out, acc * inv_total);
@@ -636,6 +674,7 @@ __global__ void rmsprop_kernel(float* __restrict__ p32, bf16* __restrict__ p16,
 using namespace cc;
 
 #define ST(s) ((cudaStream_t)(s))
+#define F32(mask, bit) (((mask) >> (bit)) & 1)
 #define EW_LAUNCH(kern, rows, cols, stream, ...)                                        \
   do {                                                                                  \
     if ((rows) <= 0 || (cols) <= 0) return 0;                                           \
@@ -645,8 +684,8 @@ using namespace cc;
     return 0;                                                                           \
   } while (0)
 
-extern "C" int cc_colsum(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* out,
-                         int32_t beta, cc_stream_t stream) {
+extern "C" int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
+                         int32_t beta, int32_t dtypes, cc_stream_t stream) {
   if (cols <= 0) return 0;
   if (rows <= 0) {
     if (!beta) {
@@ -655,17 +694,38 @@ extern "C" int cc_colsum(const void* x16, int64_t ld, int64_t rows, int64_t cols
     }
     return 0;
   }
-  return launch_colreduce<0>((const bf16*)x16, ld, nullptr, 0, rows, cols, nullptr, nullptr, out,
-                             beta, ST(stream));
+  return launch_colreduce<0>(mat(x, ld, F32(dtypes, 0)), mat(nullptr, 0, 0), rows, cols, nullptr,
+                             nullptr, out, beta, ST(stream));
 }
 
-extern "C" int cc_dropout(const void* x16, int64_t ldx, void* out16, int64_t ldo, int64_t rows,
+extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
+                            int64_t cols, int32_t act, float* out, int32_t dtypes,
+                            cc_stream_t stream) {
+  if (cols <= 0) return 0;
+  if (rows <= 0) {
+    fill_f32_kernel<<<ew_grid(cols, 256), 256, 0, ST(stream)>>>(out, 0.f, cols);
+    CC_CHECK_LAUNCH();
+    return 0;
+  }
+  return launch_colreduce<3>(mat(dy, lddy, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), rows, cols,
+                             nullptr, nullptr, out, 0, ST(stream), act);
+}
+
+extern "C" int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo,
+                             int64_t ldlo, int64_t rows, int64_t cols, int32_t dtypes,
+                             cc_stream_t stream) {
+  EW_LAUNCH(split_kernel, rows, cols, stream, mat(x, ldx, F32(dtypes, 0)), mat(hi, ldhi, 0),
+            mat(lo, ldlo, 0), rows, cols);
+}
+
+extern "C" int cc_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows,
                           int64_t cols, float rate, const uint8_t* mask_u8, int64_t ldm,
                           uint64_t seed, const uint64_t* counter_dev, uint32_t stream_id,
-                          cc_stream_t stream) {
+                          int32_t dtypes, cc_stream_t stream) {
   CC_REQUIRE(rate >= 0.f && rate < 1.f, "cc_dropout: rate %f out of range", rate);
-  EW_LAUNCH(dropout_kernel, rows, cols, stream, (const bf16*)x16, ldx, (bf16*)out16, ldo, rows,
-            cols, rate, mask_u8, ldm, seed, counter_dev, stream_id);
+  EW_LAUNCH(dropout_kernel, rows, cols, stream, mat(x, ldx, F32(dtypes, 0)),
+            mat(out, ldo, F32(dtypes, 1)), rows, cols, rate, mask_u8, ldm, seed, counter_dev,
+            stream_id);
 }
 
 extern "C" int cc_dropout_mask(uint8_t* mask_u8, int64_t ldm, int64_t rows, int64_t cols,
@@ -688,74 +748,65 @@ extern "C" int cc_counter_add(uint64_t* counter_dev, uint64_t inc, cc_stream_t s
   return 0;
 }
 
-extern "C" int cc_act_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy, void* dz16,
-                          int64_t lddz, int64_t rows, int64_t cols, int32_t act,
+extern "C" int cc_act_bwd(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dz,
+                          int64_t lddz, int64_t rows, int64_t cols, int32_t act, int32_t dtypes,
                           cc_stream_t stream) {
-  EW_LAUNCH(act_bwd_kernel, rows, cols, stream, (const bf16*)dy16, lddy, (const bf16*)y16, ldy,
-            (bf16*)dz16, lddz, rows, cols, act);
+  EW_LAUNCH(act_bwd_kernel, rows, cols, stream, mat(dy, lddy, F32(dtypes, 0)),
+            mat(y, ldy, F32(dtypes, 1)), mat(dz, lddz, F32(dtypes, 2)), rows, cols, act);
 }
 
-extern "C" int cc_copy2d(const void* src16, int64_t lds, void* dst16, int64_t ldd, int64_t rows,
-                         int64_t cols, int32_t beta, cc_stream_t stream) {
-  EW_LAUNCH(copy2d_kernel, rows, cols, stream, (const bf16*)src16, lds, (bf16*)dst16, ldd, rows,
-            cols, beta);
+extern "C" int cc_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows,
+                         int64_t cols, int32_t beta, float scale, int32_t dtypes,
+                         cc_stream_t stream) {
+  EW_LAUNCH(copy2d_kernel, rows, cols, stream, mat(src, lds, F32(dtypes, 0)),
+            mat(dst, ldd, F32(dtypes, 1)), rows, cols, beta, scale);
 }
 
-extern "C" int cc_cast_f32_to_bf16(const float* src, int64_t lds, void* dst16, int64_t ldd,
-                                   int64_t rows, int64_t cols, cc_stream_t stream) {
-  EW_LAUNCH(cast_f32_bf16_kernel, rows, cols, stream, src, lds, (bf16*)dst16, ldd, rows, cols);
-}
-
-extern "C" int cc_cast_bf16_to_f32(const void* src16, int64_t lds, float* dst, int64_t ldd,
-                                   int64_t rows, int64_t cols, float scale, cc_stream_t stream) {
-  EW_LAUNCH(cast_bf16_f32_kernel, rows, cols, stream, (const bf16*)src16, lds, dst, ldd, rows,
-            cols, scale);
-}
-
-extern "C" int cc_bn_stats(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* sums,
-                           cc_stream_t stream) {
+extern "C" int cc_bn_stats(const void* x, int64_t ld, int64_t rows, int64_t cols, float* sums,
+                           int32_t dtypes, cc_stream_t stream) {
   if (cols <= 0) return 0;
   CC_REQUIRE(rows > 0, "cc_bn_stats: empty batch");
-  return launch_colreduce<1>((const bf16*)x16, ld, nullptr, 0, rows, cols, nullptr, nullptr, sums,
-                             0, ST(stream));
+  return launch_colreduce<1>(mat(x, ld, F32(dtypes, 0)), mat(nullptr, 0, 0), rows, cols, nullptr,
+                             nullptr, sums, 0, ST(stream));
 }
 
-extern "C" int cc_bn_train_apply(const void* x16, int64_t ldx, void* y16, int64_t ldy,
-                                 int64_t rows, int64_t cols, const float* sums, int64_t n_total,
+extern "C" int cc_bn_train_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows,
+                                 int64_t cols, const float* sums, int64_t n_total,
                                  const float* gamma, const float* beta, float eps, float momentum,
                                  float* moving_mean, float* moving_var, float* save_mean,
-                                 float* save_rstd, cc_stream_t stream) {
+                                 float* save_rstd, int32_t dtypes, cc_stream_t stream) {
   if (cols <= 0) return 0;
   CC_REQUIRE(n_total > 0, "cc_bn_train_apply: n_total must be positive");
   bn_finalize_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, ST(stream)>>>(
       sums, cols, 1.0 / (double)n_total, eps, momentum, moving_mean, moving_var, save_mean,
       save_rstd);
   CC_CHECK_LAUNCH();
-  EW_LAUNCH(bn_apply_kernel, rows, cols, stream, (const bf16*)x16, ldx, (bf16*)y16, ldy, rows,
-            cols, gamma, beta, save_mean, save_rstd, 0, eps);
+  EW_LAUNCH(bn_apply_kernel, rows, cols, stream, mat(x, ldx, F32(dtypes, 0)),
+            mat(y, ldy, F32(dtypes, 1)), rows, cols, gamma, beta, save_mean, save_rstd, 0, eps);
 }
 
-extern "C" int cc_bn_infer(const void* x16, int64_t ldx, void* y16, int64_t ldy, int64_t rows,
+extern "C" int cc_bn_infer(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows,
                            int64_t cols, const float* gamma, const float* beta,
                            const float* moving_mean, const float* moving_var, float eps,
-                           cc_stream_t stream) {
-  EW_LAUNCH(bn_apply_kernel, rows, cols, stream, (const bf16*)x16, ldx, (bf16*)y16, ldy, rows,
-            cols, gamma, beta, moving_mean, moving_var, 1, eps);
+                           int32_t dtypes, cc_stream_t stream) {
+  EW_LAUNCH(bn_apply_kernel, rows, cols, stream, mat(x, ldx, F32(dtypes, 0)),
+            mat(y, ldy, F32(dtypes, 1)), rows, cols, gamma, beta, moving_mean, moving_var, 1, eps);
 }
 
-extern "C" int cc_bn_bwd_stats(const void* dy16, int64_t lddy, const void* x16, int64_t ldx,
+extern "C" int cc_bn_bwd_stats(const void* dy, int64_t lddy, const void* x, int64_t ldx,
                                int64_t rows, int64_t cols, const float* save_mean,
-                               const float* save_rstd, float* sums2, cc_stream_t stream) {
+                               const float* save_rstd, float* sums2, int32_t dtypes,
+                               cc_stream_t stream) {
   if (cols <= 0) return 0;
   CC_REQUIRE(rows > 0, "cc_bn_bwd_stats: empty batch");
-  return launch_colreduce<2>((const bf16*)dy16, lddy, (const bf16*)x16, ldx, rows, cols, save_mean,
-                             save_rstd, sums2, 0, ST(stream));
+  return launch_colreduce<2>(mat(dy, lddy, F32(dtypes, 0)), mat(x, ldx, F32(dtypes, 1)), rows, cols,
+                             save_mean, save_rstd, sums2, 0, ST(stream));
 }
 
-extern "C" int cc_bn_bwd_apply(const void* dy16, int64_t lddy, const void* x16, int64_t ldx,
-                               void* dx16, int64_t lddx, int64_t rows, int64_t cols,
-                               const float* gamma, const float* save_mean, const float* save_rstd,
-                               const float* sums2, int64_t n_total, float* dgamma, float* dbeta,
+extern "C" int cc_bn_bwd_apply(const void* dy, int64_t lddy, const void* x, int64_t ldx, void* dx,
+                               int64_t lddx, int64_t rows, int64_t cols, const float* gamma,
+                               const float* save_mean, const float* save_rstd, const float* sums2,
+                               int64_t n_total, float* dgamma, float* dbeta, int32_t dtypes,
                                cc_stream_t stream) {
   if (cols <= 0) return 0;
   if (dgamma || dbeta) {
@@ -763,68 +814,69 @@ extern "C" int cc_bn_bwd_apply(const void* dy16, int64_t lddy, const void* x16, 
                                                                                  dgamma, dbeta);
     CC_CHECK_LAUNCH();
   }
-  if (dx16 == nullptr) return 0;
-  EW_LAUNCH(bn_bwd_apply_kernel, rows, cols, stream, (const bf16*)dy16, lddy, (const bf16*)x16,
-            ldx, (bf16*)dx16, lddx, rows, cols, gamma, save_mean, save_rstd, sums2,
-            1.f / (float)n_total);
+  if (dx == nullptr) return 0;
+  EW_LAUNCH(bn_bwd_apply_kernel, rows, cols, stream, mat(dy, lddy, F32(dtypes, 0)),
+            mat(x, ldx, F32(dtypes, 1)), mat(dx, lddx, F32(dtypes, 2)), rows, cols, gamma,
+            save_mean, save_rstd, sums2, 1.f / (float)n_total);
 }
 
-extern "C" int cc_bn_infer_bwd(const void* dy16, int64_t lddy, void* dx16, int64_t lddx,
-                               int64_t rows, int64_t cols, const float* gamma,
-                               const float* moving_var, float eps, cc_stream_t stream) {
-  EW_LAUNCH(bn_infer_bwd_kernel, rows, cols, stream, (const bf16*)dy16, lddy, (bf16*)dx16, lddx,
-            rows, cols, gamma, moving_var, eps);
+extern "C" int cc_bn_infer_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows,
+                               int64_t cols, const float* gamma, const float* moving_var,
+                               float eps, int32_t dtypes, cc_stream_t stream) {
+  EW_LAUNCH(bn_infer_bwd_kernel, rows, cols, stream, mat(dy, lddy, F32(dtypes, 0)),
+            mat(dx, lddx, F32(dtypes, 1)), rows, cols, gamma, moving_var, eps);
 }
 
-extern "C" int cc_softmax_fwd(const void* x16, int64_t ldx, void* y16, int64_t ldy, float* y32,
-                              int64_t ldy32, int64_t rows, int64_t cols, cc_stream_t stream) {
+extern "C" int cc_softmax_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, float* y32,
+                              int64_t ldy32, int64_t rows, int64_t cols, int32_t dtypes,
+                              cc_stream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
   softmax_fwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ST(stream)>>>(
-      (const bf16*)x16, ldx, (bf16*)y16, ldy, y32, ldy32, rows, cols);
+      mat(x, ldx, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), y32, ldy32, rows, cols);
   CC_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int cc_softmax_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy,
-                              void* dx16, int64_t lddx, int64_t rows, int64_t cols,
+extern "C" int cc_softmax_bwd(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dx,
+                              int64_t lddx, int64_t rows, int64_t cols, int32_t dtypes,
                               cc_stream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
   softmax_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, ST(stream)>>>(
-      (const bf16*)dy16, lddy, (const bf16*)y16, ldy, (bf16*)dx16, lddx, rows, cols);
+      mat(dy, lddy, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), mat(dx, lddx, F32(dtypes, 2)),
+      rows, cols);
   CC_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int cc_bce_fwd_bwd(const float* x32, int64_t ldx, int64_t rows, int32_t from_logits,
-                              float target, int64_t n_total, float* loss_out, void* dz16,
-                              int64_t lddz, cc_stream_t stream) {
+                              float target, int64_t n_total, float* loss_out, void* dz,
+                              int64_t lddz, int32_t dtypes, cc_stream_t stream) {
   CC_REQUIRE(rows > 0 && n_total > 0, "cc_bce_fwd_bwd: empty batch");
   bce_kernel<<<1, 256, 0, ST(stream)>>>(x32, ldx, rows, from_logits, target, 1.f / (float)n_total,
-                                        loss_out, (bf16*)dz16, lddz);
+                                        loss_out, mat(dz, lddz, F32(dtypes, 0)));
   CC_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int cc_mse_fwd_bwd(const void* pred16, int64_t ldp, const void* target16, int64_t ldt,
-                              const float* target32, int64_t ldt32, int64_t rows, int64_t cols,
-                              int64_t n_total, float* loss_out, void* dpred16, int64_t lddp,
-                              cc_stream_t stream) {
-  CC_REQUIRE(target16 != nullptr || target32 != nullptr, "cc_mse_fwd_bwd: no target");
+extern "C" int cc_mse_fwd_bwd(const void* pred, int64_t ldp, const void* target, int64_t ldt,
+                              int64_t rows, int64_t cols, int64_t n_total, float* loss_out,
+                              void* dpred, int64_t lddp, int32_t dtypes, cc_stream_t stream) {
+  CC_REQUIRE(target != nullptr, "cc_mse_fwd_bwd: no target");
   if (rows <= 0 || cols <= 0) return 0;
   const float inv_total = 1.f / ((float)n_total * (float)cols);
   const long long work = (long long)rows * ((cols + 7) / 8);
   mse_kernel<<<ew_grid(work, 256), 256, 0, ST(stream)>>>(
-      (const bf16*)pred16, ldp, (const bf16*)target16, ldt, target32, ldt32, rows, cols, inv_total,
-      loss_out, (bf16*)dpred16, lddp);
+      mat(pred, ldp, F32(dtypes, 0)), mat(target, ldt, F32(dtypes, 1)), rows, cols, inv_total,
+      loss_out, mat(dpred, lddp, F32(dtypes, 2)));
   CC_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int cc_round_half_even(const void* x16, int64_t ldx, void* out16, int64_t ldo,
-                                  float* out32, int64_t ldo32, int64_t rows, int64_t cols,
+extern "C" int cc_round_half_even(const void* x, int64_t ldx, void* out, int64_t ldo, float* out32,
+                                  int64_t ldo32, int64_t rows, int64_t cols, int32_t dtypes,
                                   cc_stream_t stream) {
-  EW_LAUNCH(round_kernel, rows, cols, stream, (const bf16*)x16, ldx, (bf16*)out16, ldo, out32,
-            ldo32, rows, cols);
+  EW_LAUNCH(round_kernel, rows, cols, stream, mat(x, ldx, F32(dtypes, 0)),
+            mat(out, ldo, F32(dtypes, 1)), out32, ldo32, rows, cols);
 }
 
 extern "C" int cc_argmax_onehot(const float* p32, int64_t ldp, void* out16, int64_t ldo,

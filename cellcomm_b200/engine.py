@@ -13,6 +13,7 @@ Semantics follow Keras 2.4.0 as used by the reference:
   * Dropout: active inside frozen sub-models during train_on_batch, off in predict.
 """
 import math
+import os
 
 import torch
 
@@ -26,6 +27,14 @@ LR, RHO, MOMENTUM, EPSILON = 0.0075, 0.85, 0.1, 1e-7   # src/bigan_classify.py:8
 REAL_LABEL = 0.95                                 # src/bigan_classify.py:128
 
 _ACT = {"none": 0, "sigmoid": 1, "relu": 2, "softmax": 0}
+# two-term bf16 expansion for the inputs of Dense layers that feed a BatchNormalization
+# 0: none; 1: narrow tensors only (free); 2: also the wide inputs of BN-feeding Dense layers;
+# 3: also their dL/dz.  Default "auto": level 3 for the generator (its relu+BN trunk is the
+# only place where bf16 operands cost more than 2 % gradient cosine; +3.4 % GEMM work per
+# step), level 1 for E and D.  Level 3 everywhere costs +17 %.  See DESIGN.md.
+_SPLIT_ENV = os.environ.get("CELLCOMM_B200_SPLIT", "auto")
+_SPLIT_PRECISION = None if _SPLIT_ENV == "auto" else int(_SPLIT_ENV)
+_SMALL_WIDTH = int(os.environ.get("CELLCOMM_B200_SMALL_WIDTH", "512"))
 
 
 # =========================================================================== graph specs
@@ -192,16 +201,21 @@ class Net:
     """One network (G, E or D): parameters in flat fused-layout buffers, activation buffers for
     up to `max_rows` rows, forward / backward / RMSprop."""
 
-    def __init__(self, graph, max_rows, device, generator=None, dist=None):
+    def __init__(self, graph, max_rows, device, generator=None, dist=None, precision=1):
+        self.precision = precision if _SPLIT_PRECISION is None else _SPLIT_PRECISION
         self.g = graph
         self.name = graph.name
         self.max_rows = int(max_rows)
         self.device = device
         self.dist = dist or _NoDist()
         self._alloc_params(generator)
-        self.act = {}
-        self.grad = {}
-        self.tmp = {}
+        self.act = {}      # forward activations (bf16; fp32 for tensors in self.hp)
+        self.shadow = {}   # bf16 copies of fp32 activations that also feed a GEMM
+        self.grad = {}     # activation gradients, always fp32
+        self.tmp = {}      # fp32 scratch for accumulating a second gradient contribution
+        self.dzb = {}      # bf16 gradient w.r.t. a Dense pre-activation (GEMM operand)
+        self.hp, self.split = self._high_precision_tensors()
+        self.split_lo = {}  # bf16 low-order terms of the split tensors
         self._needs_cache = {}
         self._ctx = None
         self.logits32 = None
@@ -227,7 +241,7 @@ class Net:
         self.g32 = torch.zeros_like(self.p32)
         self.ms = torch.zeros_like(self.p32)
         self.mom = torch.zeros_like(self.p32)
-        self.p16 = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=dev)
+        self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
         self.layers = []
         for m in meta:
             L = dict(m)
@@ -299,13 +313,120 @@ class Net:
         self.mom.zero_()
         self.sync_compute_copy()
 
+    # ------------------------------------------------------------------ precision policy
+    def _high_precision_tensors(self):
+        """(hp, split): tensors stored in fp32, and the subset consumed by GEMMs as a two-term
+        bf16 expansion (hi + lo segments).
+
+        BatchNormalization divides by the batch standard deviation, which for sigmoid features
+        is ~0.02-0.05 while bf16 resolves values near 0.5 to only 0.002-0.004, so 16-bit
+        storage on the way INTO a BN costs several percent of the signal (measured against the
+        oracle: gradient cosines of 0.3-0.97; see DESIGN.md "precision policy").  Hence
+          * everything from a Dense output to a BN input (through Dropout / Concatenate) is fp32;
+          * the inputs of those Dense layers are fp32 too and enter the GEMM as hi + lo.
+        Network inputs stay as fed."""
+        g = self.g
+        producer = {n["out"]: n for n in g.nodes}
+
+        def closure(seeds):
+            out, stack = set(), list(seeds)
+            while stack:
+                t = stack.pop()
+                n = producer.get(t)
+                if n is None or t in out:
+                    continue
+                out.add(t)
+                if n["kind"] in ("dropout", "concat"):
+                    stack.extend(n["ins"])
+            return out
+
+        hp = closure(n["ins"][0] for n in g.nodes if n["kind"] == "bn")
+        split = set()
+        # Dense outputs on the way into a BN: their dL/dz (the BN-backward output) sums to ~0
+        # over the batch, so wgrad / dgrad / the bias gradient of the layer below are
+        # cancellation-dominated and need dz as hi + lo as well.
+        self.prebn = set()
+        if self.precision >= 2:
+            for n in g.nodes:
+                if n["kind"] == "dense" and n["out"] in hp:
+                    if self.precision >= 3:
+                        self.prebn.add(n["out"])
+                    split.update(i for i in n["ins"] if i in producer and g.widths[i] > 0)
+        if self.precision >= 1:
+            # narrow tensors (latents, the 50..256-wide trunks, the encoder tail): fp32 + hi/lo
+            # costs nothing and keeps the small-variance sigmoid features exact
+            for n in g.nodes:
+                if 0 < g.widths[n["out"]] <= _SMALL_WIDTH:
+                    split.add(n["out"])
+                    if n["kind"] == "dense":
+                        self.prebn.add(n["out"])
+        return hp | closure(split), split
+
+    def get_slots(self):
+        """RMSprop slots (ms, mom) per trainable tensor in creation order (kernel, bias | gamma,
+        beta), as host arrays: checkpointing and parity tests."""
+        out = []
+        for L in self.layers:
+            for key in (("w32", "b32") if L["kind"] == "dense" else ("gamma", "beta")):
+                out.append((self._like(L[key], self.ms).detach().cpu().numpy().copy(),
+                            self._like(L[key], self.mom).detach().cpu().numpy().copy()))
+        return out
+
+    def set_slots(self, slots):
+        it = iter(slots)
+        for L in self.layers:
+            for key in (("w32", "b32") if L["kind"] == "dense" else ("gamma", "beta")):
+                ms, mom = next(it)
+                if L[key].numel():
+                    self._like(L[key], self.ms).copy_(torch.as_tensor(ms, dtype=torch.float32))
+                    self._like(L[key], self.mom).copy_(torch.as_tensor(mom, dtype=torch.float32))
+
+    def _like(self, view, flat):
+        """The view of `flat` (ms / mom / g32) laid out like the parameter view `view` of p32."""
+        off = view.storage_offset() - self.p32.storage_offset()
+        return torch.as_strided(flat, view.shape, view.stride(), flat.storage_offset() + off)
+
     # ------------------------------------------------------------------ buffers
-    def _buf(self, store, tid, dtype=torch.bfloat16):
+    def reserve(self, rows):
+        """Grow the activation/gradient buffers to hold `rows` rows (drops the old ones)."""
+        if rows > self.max_rows:
+            self.max_rows = int(rows)
+            self.act, self.grad, self.tmp, self.shadow, self.dzb = {}, {}, {}, {}, {}
+            self.split_lo = {}
+            self.logits32 = None
+            self._ctx = None
+
+    def _buf(self, store, tid):
         b = store.get(tid)
         if b is None:
-            b = ops.alloc2d(self.max_rows, self.g.widths[tid], dtype=dtype, device=self.device)
+            wid = tid[1] if isinstance(tid, tuple) else tid
+            if store is self.grad or store is self.tmp or (store is self.act and tid in self.hp):
+                dtype = torch.float32
+            else:
+                dtype = ops.COMPUTE_DTYPE
+            b = ops.alloc2d(self.max_rows, self.g.widths[wid], dtype=dtype, device=self.device)
             store[tid] = b
         return b
+
+    def _gemm_operands(self, A, tid, rows):
+        """bf16 GEMM operand(s) for activation `tid`: [x] for bf16 tensors, [hi, lo] for split
+        tensors, [bf16 copy] for other fp32 tensors (prepared once per forward)."""
+        ops_ = self._ctx_operands.get(tid)
+        if ops_ is None:
+            x = A[tid]
+            if x.dtype != torch.float32:
+                ops_ = [x]
+            elif tid in self.split:
+                hi = self._buf(self.shadow, tid)[:rows]
+                lo = self._buf(self.split_lo, tid)[:rows]
+                ops.split_bf16(x, hi, lo)
+                ops_ = [hi, lo]
+            else:
+                sh = self._buf(self.shadow, tid)[:rows]
+                ops.copy2d(x, sh)
+                ops_ = [sh]
+            self._ctx_operands[tid] = ops_
+        return ops_
 
     def _needs(self, train, want):
         key = (bool(train), tuple(sorted(want)))
@@ -326,8 +447,7 @@ class Net:
         """feed: {input name: [rows, width] bf16 view}.  dropout: 'off' (predict), 'masks'
         (explicit uint8 keep-masks in call order) or 'rng' (rng = (seed, counter, base_id)).
         Returns the output activation ([rows, width] bf16), or fp32 logits when pre_activation."""
-        if rows > self.max_rows:
-            raise ValueError(f"{self.name}: batch of {rows} rows exceeds max_rows={self.max_rows}")
+        self.reserve(rows)
         g = self.g
         A = {}
         for name, t in g.inputs.items():
@@ -338,6 +458,7 @@ class Net:
             A[t] = x
         n_total = rows * self.dist.world_size
         last = g.nodes[-1]
+        self._ctx_operands = {}
         for node in g.nodes:
             kind, out = node["kind"], node["out"]
             width = g.widths[out]
@@ -345,26 +466,33 @@ class Net:
                 L = self.layers[node["layer"]]
                 y = self._buf(self.act, out)[:rows]
                 is_last = node is last or (last["kind"] == "softmax" and last["ins"][0] == out)
-                o32 = None
                 act = _ACT[node["act"]]
+                wants_out32 = is_last and out32 is not None and last["kind"] != "softmax"
+                dest16, dest32, copy_out = y, None, None
                 if is_last and pre_activation:
                     if self.logits32 is None:
                         self.logits32 = ops.alloc2d(self.max_rows, width, dtype=torch.float32,
                                                     device=self.device)
-                    o32, act = self.logits32[:rows], 0
-                elif is_last and out32 is not None and last["kind"] != "softmax":
-                    o32 = out32
+                    dest16, dest32, act = None, self.logits32[:rows], 0
+                elif y.dtype == torch.float32:           # fp32 activation (precision policy)
+                    dest16, dest32 = None, y
+                    copy_out = out32 if wants_out32 else None
+                elif wants_out32:
+                    dest32 = out32
                 if width > 0:
                     xs, offs, ro = [], [], 0
                     for i in node["ins"]:
                         if g.widths[i] > 0:
-                            xs.append(A[i])
-                            offs.append(ro)
+                            for term in self._gemm_operands(A, i, rows):
+                                xs.append(term)
+                                offs.append(ro)
                         ro += g.widths[i]
                     if xs:
-                        ops.dense_fwd(xs, L["w16"], offs, L["b32"], act, out16=y, out32=o32)
+                        ops.dense_fwd(xs, L["w16"], offs, L["b32"], act, out16=dest16, out32=dest32)
                     else:
-                        ops.bias_act(L["b32"], act, rows, out16=y, out32=o32)
+                        ops.bias_act(L["b32"], act, rows, out16=dest16, out32=dest32)
+                    if copy_out is not None:
+                        ops.copy2d(y, copy_out)
                 A[out] = y
             elif kind == "softmax":
                 y = self._buf(self.act, out)[:rows]
@@ -405,7 +533,8 @@ class Net:
                     c += w
                 A[out] = y
         self._ctx = {"rows": rows, "bn_train": bn_train, "dropout": dropout, "masks": masks,
-                     "rng": rng, "A": A, "pre_activation": pre_activation, "n_total": n_total}
+                     "rng": rng, "A": A, "pre_activation": pre_activation, "n_total": n_total,
+                     "operands": self._ctx_operands}
         if pre_activation:
             return self.logits32[:rows]
         return A[g.output]
@@ -434,6 +563,11 @@ class Net:
             fn(t)
             ops.copy2d(t, dst, beta=1)
 
+    def output_grad(self, rows):
+        """fp32 buffer for dL/d(output); a loss kernel may write it in place and pass it to
+        backward(), which then skips the seed copy."""
+        return self._buf(self.grad, self.g.output)[:rows]
+
     def backward(self, dout, *, train, want=()):
         """dout: gradient w.r.t. the output (bf16 [rows, width]); for a pre_activation forward it
         is the gradient w.r.t. the final layer's logits.  train=True fills this net's parameter
@@ -443,9 +577,9 @@ class Net:
         needs = self._needs(train, want)
         state = [False] * len(g.widths)
         out_t = g.output
-        self._buf(self.grad, out_t)
-        if g.widths[out_t] > 0:
-            ops.copy2d(dout, self.grad[out_t][:rows])
+        seed = self._buf(self.grad, out_t)[:rows]
+        if g.widths[out_t] > 0 and dout.data_ptr() != seed.data_ptr():
+            ops.copy2d(dout, seed)
         state[out_t] = True
         last = g.nodes[-1]
         for node in reversed(g.nodes):
@@ -460,23 +594,41 @@ class Net:
                     continue
                 is_last = node is last or (last["kind"] == "softmax" and last["ins"][0] == out)
                 act = _ACT[node["act"]]
-                if act != 0 and not (is_last and c["pre_activation"]):
-                    ops.act_bwd(dy, A[out], dy, act)      # dz in place
-                dz = dy
+                if is_last and c["pre_activation"]:
+                    act = 0
+                # fp32 dL/dy -> bf16 dL/dz = dy * act'(y): the GEMM operand of wgrad / dgrad
+                dz = self._buf(self.dzb, out)[:rows]
+                if out in self.prebn:
+                    ops.act_bwd(dy, A[out], dy, act)              # fp32, in place
+                    dz_lo = self._buf(self.split_lo, ("dz", out))[:rows]
+                    ops.split_bf16(dy, dz, dz_lo)
+                    dzs = [dz, dz_lo]
+                else:
+                    ops.act_bwd(dy, A[out], dz, act)
+                    dzs = [dz]
                 ro = 0
                 for i in node["ins"]:
                     k = g.widths[i]
                     if k > 0:
                         if train:
-                            ops.dense_wgrad(A[i], dz, L["dw"][ro:ro + k])
+                            xs = c["operands"][i]
+                            # all hi/lo cross terms except lo*lo
+                            pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
+                                     if a + b < 2]
+                            ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs],
+                                            L["dw"][ro:ro + k])
                         if needs[i]:
                             wseg = L["w16"][ro:ro + k]
                             dst = self._buf(self.grad, i)[:rows]
-                            ops.dense_dgrad([dz], [wseg], dst, beta=1 if state[i] else 0)
+                            ops.dense_dgrad(dzs, [wseg] * len(dzs), dst,
+                                            beta=1 if state[i] else 0)
                             state[i] = True
                     ro += k
                 if train:
-                    ops.colsum(dz, L["db"])
+                    if out in self.prebn:
+                        ops.bias_grad(dy, A[out], 0, L["db"])     # dy already holds dz (fp32)
+                    else:
+                        ops.bias_grad(dy, A[out], act, L["db"])
             elif kind == "softmax":
                 i = node["ins"][0]
                 if width > 0 and needs[i]:
@@ -526,7 +678,8 @@ class Net:
         for name in want:
             t = g.inputs[name]
             if not state[t]:
-                raise RuntimeError(f"{self.name}: no gradient reached input '{name}'")
+                # zero-width layers (the 5-gene fixture's Dense(0)) cut the path: gradient is 0
+                self._buf(self.grad, t).zero_()
             grads[name] = self.grad[t][:rows]
         return grads
 
@@ -601,38 +754,51 @@ class BiGanEngine:
                     8: ("D",)}
 
     def __init__(self, variant, encoding_size, gene_size, max_batch=128, device="cuda", seed=None,
-                 dist=None):
+                 dist=None, graphs=None):
+        """variant 'cont' | 'classify' picks the reference graphs and whether sub-step 7 feeds
+        one_hot(argmax) (classify, src/bigan_classify.py:121-124) or the raw encoding (cont,
+        src/bigan_cont.py:55-56) to D.  `graphs` = {"G","E","D": GraphBuilder} overrides them."""
         if variant not in ("cont", "classify"):
             raise ValueError(f"unknown variant {variant}")
         self.variant, self.Z, self.Gn = variant, int(encoding_size), int(gene_size)
         self.device = torch.device(device)
-        self.max_batch = int(max_batch)
         self.dist = dist or _NoDist()
         gen = torch.Generator()
         if seed is None:
             gen.seed()
         else:
             gen.manual_seed(int(seed))
-        gg = cont_generator_graph if variant == "cont" else classify_generator_graph
-        eg = cont_encoder_graph if variant == "cont" else classify_encoder_graph
-        self.G = Net(gg(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
-        self.E = Net(eg(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
-        self.D = Net(discriminator_graph(self.Z, self.Gn), max_batch, self.device, gen, self.dist)
+        if graphs is None:
+            gg = cont_generator_graph if variant == "cont" else classify_generator_graph
+            eg = cont_encoder_graph if variant == "cont" else classify_encoder_graph
+            graphs = {"G": gg(self.Z, self.Gn), "E": eg(self.Z, self.Gn),
+                      "D": discriminator_graph(self.Z, self.Gn)}
+        self.G = Net(graphs["G"], max_batch, self.device, gen, self.dist, precision=3)
+        self.E = Net(graphs["E"], max_batch, self.device, gen, self.dist)
+        self.D = Net(graphs["D"], max_batch, self.device, gen, self.dist)
         self.nets = {"G": self.G, "E": self.E, "D": self.D}
         self.loss_buf = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
-        mb, Z, Gn = self.max_batch, self.Z, self.Gn
-        self.z16 = ops.alloc2d(mb, Z, device=self.device)
-        self.r16 = ops.alloc2d(mb, Z, device=self.device)
-        self.z32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
-        self.r32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
-        self.dz1 = ops.alloc2d(mb, 1, device=self.device)
-        self.dgen = None
-        self.denc = ops.alloc2d(mb, Z, device=self.device)
+        self.max_batch = 0
+        self.reserve(max_batch)
+
+    def reserve(self, rows):
+        """(Re)allocate the per-step staging buffers for batches of up to `rows` rows."""
+        rows = int(rows)
+        if rows <= self.max_batch:
+            return
+        self.max_batch = mb = rows
+        Z, dev = self.Z, self.device
+        for n in self.nets.values():
+            n.reserve(mb)
+        self.z16 = ops.alloc2d(mb, Z, device=dev)
+        self.r16 = ops.alloc2d(mb, Z, device=dev)
+        self.z32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=dev)
+        self.r32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=dev)
         self.gen_cells = None
-        self.gen_enc16 = ops.alloc2d(mb, Z, device=self.device)
-        self.gen_enc32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=self.device)
+        self.gen_enc16 = ops.alloc2d(mb, Z, device=dev)
+        self.gen_enc32 = ops.alloc2d(mb, Z, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ helpers
     def _drop_args(self, substep, net, masks):
@@ -643,6 +809,7 @@ class BiGanEngine:
 
     def set_latents(self, encodings, noise, rows):
         """Stage the step's prior samples (host or device, fp32) as fp32 + bf16 device views."""
+        self.reserve(rows)
         z32, r32 = self.z32[:rows], self.r32[:rows]
         z32.copy_(torch.as_tensor(encodings, dtype=torch.float32), non_blocking=True)
         r32.copy_(torch.as_tensor(noise, dtype=torch.float32), non_blocking=True)
@@ -651,6 +818,7 @@ class BiGanEngine:
 
     def draw_latents(self, rows):
         """tf.random.uniform priors on the device (src/bigan_basic.py:36-37, bigan_cont.py:52-53)."""
+        self.reserve(rows)
         ops.uniform(out32=self.z32[:rows], out16=self.z16[:rows], seed=self.rng_seed,
                     counter=self.rng_counter, stream_id=1000)
         ops.uniform(out32=self.r32[:rows], out16=self.r16[:rows], seed=self.rng_seed,
@@ -661,73 +829,91 @@ class BiGanEngine:
         """One `trainings_step` on the batch x16 ([B, gene_size] bf16 view).  The priors must
         have been staged with set_latents()/draw_latents().  Returns (g, e, d) LossScalars."""
         B = x16.shape[0]
-        z, r = self.z16[:B], self.r16[:B]
+        if B > self.max_batch:
+            raise ValueError(f"batch of {B} rows: stage the priors (set_latents/draw_latents) first")
+        ops.fill_f32(self.loss_buf, 0.0)
+        for k in (1, 2, 3, 4, 5, 6, 7, 8):
+            self.substep(k, x16, masks)
+        return self.finish_step(masks)
+
+    def substep(self, k, x16, masks=None):
+        """Sub-step k (1..8) of `trainings_step`, src/bigan_classify.py:126-155 (numbering of
+        SURVEY.md 3.2).  Exposed separately so the parity tests can compare every update
+        against the oracle from identical weights."""
+        B = x16.shape[0]
+        z, r = self.z32[:B], self.r32[:B]          # latents stay fp32 (hi/lo in the GEMMs)
         G, E, D = self.G, self.E, self.D
         n_total = B * self.dist.world_size
         L = self.loss_buf
-        ops.fill_f32(L, 0.0)
-        if self.dgen is None:
-            self.dgen = ops.alloc2d(self.max_batch, self.Gn, device=self.device)
+        if self.gen_cells is None:
             self.gen_cells = ops.alloc2d(self.max_batch, self.Gn, device=self.device)
-        dz1, dgen, denc = self.dz1[:B], self.dgen[:B], self.denc[:B]
-
-        # (1) _train_gen_w_discr.train_on_batch((encodings, noise), y_ones)   bigan_classify.py:145
-        gen = G.forward({"z": z, "r": r}, B, bn_train=True, **self._drop_args(1, "G", masks))
-        logit = D.forward({"z": z, "cell": gen}, B, bn_train=False, pre_activation=True,
-                          **self._drop_args(1, "D", masks))
-        ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[0:1], dz1)
-        dcell = D.backward(dz1, train=False, want=("cell",))["cell"]
-        G.backward(dcell, train=True)
-        G.apply_rmsprop()
-
-        # (2) _train_gen_w_enc.train_on_batch((cell_data, noise), cell_data)  :146
-        enc = E.forward({"cell": x16}, B, bn_train=False, **self._drop_args(2, "E", masks))
-        gen = G.forward({"z": enc, "r": r}, B, bn_train=True, **self._drop_args(2, "G", masks))
-        ops.mse_fwd_bwd(gen, n_total, L[1:2], target16=x16, dpred16=dgen)
-        G.backward(dgen, train=True)
-        G.apply_rmsprop()
-
-        # (3) _train_enc_w_discr.train_on_batch(cell_data, y_zeros)           :150
-        enc = E.forward({"cell": x16}, B, bn_train=True, **self._drop_args(3, "E", masks))
-        logit = D.forward({"z": enc, "cell": x16}, B, bn_train=False, pre_activation=True,
-                          **self._drop_args(3, "D", masks))
-        ops.bce_fwd_bwd(logit, 0.0, n_total, L[2:3], dz1)
-        dzin = D.backward(dz1, train=False, want=("z",))["z"]
-        E.backward(dzin, train=True)
-        E.apply_rmsprop()
-
-        # (4) _train_enc_w_gen.train_on_batch((encodings, noise), encodings)  :151
-        gen = G.forward({"z": z, "r": r}, B, bn_train=False, **self._drop_args(4, "G", masks))
-        enc = E.forward({"cell": gen}, B, bn_train=True, **self._drop_args(4, "E", masks))
-        ops.mse_fwd_bwd(enc, n_total, L[3:4], target32=self.z32[:B], dpred16=denc)
-        E.backward(denc, train=True)
-        E.apply_rmsprop()
-
-        # (5) generated_cells = generate_cells(encodings, noise)             :136
-        gen = G.forward({"z": z, "r": r}, B, bn_train=False, dropout="off")
         cells = self.gen_cells[:B]
-        ops.round_half_even(gen, out16=cells)
+        if k == 1:
+            # _train_gen_w_discr.train_on_batch((encodings, noise), y_ones)          :145
+            gen = G.forward({"z": z, "r": r}, B, bn_train=True, **self._drop_args(1, "G", masks))
+            logit = D.forward({"z": z, "cell": gen}, B, bn_train=False, pre_activation=True,
+                              **self._drop_args(1, "D", masks))
+            dz1 = D.output_grad(B)
+            ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[0:1], dz1)
+            dcell = D.backward(dz1, train=False, want=("cell",))["cell"]
+            G.backward(dcell, train=True)
+            G.apply_rmsprop()
+        elif k == 2:
+            # _train_gen_w_enc.train_on_batch((cell_data, noise), cell_data)         :146
+            enc = E.forward({"cell": x16}, B, bn_train=False, **self._drop_args(2, "E", masks))
+            gen = G.forward({"z": enc, "r": r}, B, bn_train=True, **self._drop_args(2, "G", masks))
+            dgen = G.output_grad(B)
+            ops.mse_fwd_bwd(gen, n_total, L[1:2], target=x16, dpred=dgen)
+            G.backward(dgen, train=True)
+            G.apply_rmsprop()
+        elif k == 3:
+            # _train_enc_w_discr.train_on_batch(cell_data, y_zeros)                  :150
+            enc = E.forward({"cell": x16}, B, bn_train=True, **self._drop_args(3, "E", masks))
+            logit = D.forward({"z": enc, "cell": x16}, B, bn_train=False, pre_activation=True,
+                              **self._drop_args(3, "D", masks))
+            dz1 = D.output_grad(B)
+            ops.bce_fwd_bwd(logit, 0.0, n_total, L[2:3], dz1)
+            dzin = D.backward(dz1, train=False, want=("z",))["z"]
+            E.backward(dzin, train=True)
+            E.apply_rmsprop()
+        elif k == 4:
+            # _train_enc_w_gen.train_on_batch((encodings, noise), encodings)         :151
+            gen = G.forward({"z": z, "r": r}, B, bn_train=False, **self._drop_args(4, "G", masks))
+            enc = E.forward({"cell": gen}, B, bn_train=True, **self._drop_args(4, "E", masks))
+            denc = E.output_grad(B)
+            ops.mse_fwd_bwd(enc, n_total, L[3:4], target=self.z32[:B], dpred=denc)
+            E.backward(denc, train=True)
+            E.apply_rmsprop()
+        elif k == 5:
+            # generated_cells = generate_cells(encodings, noise)                    :136
+            gen = G.forward({"z": z, "r": r}, B, bn_train=False, dropout="off")
+            ops.round_half_even(gen, out16=cells)
+        elif k == 6:
+            # _discriminator.train_on_batch((encodings, generated_cells), y_zeros)   :137
+            logit = D.forward({"z": z, "cell": cells}, B, bn_train=True, pre_activation=True,
+                              **self._drop_args(6, "D", masks))
+            dz1 = D.output_grad(B)
+            ops.bce_fwd_bwd(logit, 0.0, n_total, L[4:5], dz1)
+            D.backward(dz1, train=True)
+            D.apply_rmsprop()
+        elif k == 7:
+            # generated_encodings = trainings_encoding_prediction(batch)            :138
+            self.encode(x16, out32=self.gen_enc32[:B])
+            if self.variant == "classify":
+                ops.argmax_onehot(self.gen_enc32[:B], out32=self.gen_enc32[:B])
+        elif k == 8:
+            # _discriminator.train_on_batch((generated_encodings, batch), y_ones)    :139
+            logit = D.forward({"z": self.gen_enc32[:B], "cell": x16}, B, bn_train=True,
+                              pre_activation=True, **self._drop_args(8, "D", masks))
+            dz1 = D.output_grad(B)
+            ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[5:6], dz1)
+            D.backward(dz1, train=True)
+            D.apply_rmsprop()
+        else:
+            raise ValueError(f"no sub-step {k}")
 
-        # (6) _discriminator.train_on_batch((encodings, generated_cells), y_zeros)   :137
-        logit = D.forward({"z": z, "cell": cells}, B, bn_train=True, pre_activation=True,
-                          **self._drop_args(6, "D", masks))
-        ops.bce_fwd_bwd(logit, 0.0, n_total, L[4:5], dz1)
-        D.backward(dz1, train=True)
-        D.apply_rmsprop()
-
-        # (7) generated_encodings = trainings_encoding_prediction(batch)     :138
-        genc = self.encode(x16, out32=self.gen_enc32[:B])
-        if self.variant == "classify":
-            ops.argmax_onehot(self.gen_enc32[:B], out16=self.gen_enc16[:B])
-            genc = self.gen_enc16[:B]
-
-        # (8) _discriminator.train_on_batch((generated_encodings, batch), y_ones)    :139
-        logit = D.forward({"z": genc, "cell": x16}, B, bn_train=True, pre_activation=True,
-                          **self._drop_args(8, "D", masks))
-        ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[5:6], dz1)
-        D.backward(dz1, train=True)
-        D.apply_rmsprop()
-
+    def finish_step(self, masks=None):
+        L = self.loss_buf
         if masks is None:
             ops.counter_add(self.rng_counter, 1)
         self.dist.all_reduce(L)
@@ -746,7 +932,7 @@ class BiGanEngine:
 
     def generate(self, rows, out32=None):
         """G.predict on the staged latents (first `rows`)."""
-        return self.G.forward({"z": self.z16[:rows], "r": self.r16[:rows]}, rows, bn_train=False,
+        return self.G.forward({"z": self.z32[:rows], "r": self.r32[:rows]}, rows, bn_train=False,
                               dropout="off", out32=out32)
 
     def discriminate(self, z16, x16, out32):

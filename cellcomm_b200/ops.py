@@ -14,6 +14,7 @@ import torch
 from . import _lib
 from ._lib import GemmDesc, check
 
+COMPUTE_DTYPE = torch.bfloat16   # GEMM operand / activation dtype
 ACT_NONE, ACT_SIGMOID, ACT_RELU = 0, 1, 2
 ACT_IDS = {None: 0, "none": 0, "linear": 0, "sigmoid": 1, "relu": 2}
 
@@ -112,20 +113,30 @@ def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
     w16: [K_total, N] bf16 Keras-layout kernel.  Dense forward, src/bigan_classify.py:10-75."""
     M, N = xs[0].shape[0], w16.shape[1]
     bs = [w16[ro:ro + x.shape[1]] for x, ro in zip(xs, row_offsets)]
+    if out16 is not None and out16.dtype == torch.float32:   # fp32 activation (feeds a BN)
+        if out32 is not None:
+            raise ValueError("dense_fwd: two fp32 outputs")
+        out16, out32 = None, out16
     gemm(M, N, xs, bs, [x.shape[1] for x in xs], 0, 1, bias=bias, act=act, out16=out16, out32=out32)
 
 
-def dense_dgrad(dzs, ws16, out16, *, dact_y=None, dact=0, alpha=1.0, beta=0):
-    """out16[M,K] (+)= alpha * (sum_s dzs[s] @ ws16[s]^T) * act'(dact_y); ws16[s]: [K, N_s]."""
-    M, K = out16.shape
+def dense_dgrad(dzs, ws16, out, *, dact_y=None, dact=0, alpha=1.0, beta=0):
+    """out[M,K] (+)= alpha * (sum_s dzs[s] @ ws16[s]^T) * act'(dact_y); ws16[s]: [K, N_s].
+    `out` is fp32 (activation gradients) or bf16."""
+    M, K = out.shape
+    kw = ({"out32": out, "beta32": beta} if out.dtype == torch.float32
+          else {"out16": out, "beta16": beta})
     gemm(M, K, dzs, ws16, [dz.shape[1] for dz in dzs], 0, 0, dact_y=dact_y, dact=dact, alpha=alpha,
-         out16=out16, beta16=beta)
+         **kw)
 
 
 def dense_wgrad(x, dz, dw32, beta=0):
-    """dw32[K,N] (+)= x[M,K]^T @ dz[M,N]."""
+    """dw32[K,N] (+)= x[M,K]^T @ dz[M,N].  x may be a list [hi, lo] (bf16 expansion): the
+    terms accumulate as GEMM segments along the batch reduction."""
     K, N = dw32.shape
-    gemm(K, N, [x], [dz], [x.shape[0]], 1, 1, out32=dw32, beta32=beta, use_ws=False)
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+    dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
+    gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta, use_ws=False)
 
 
 # --------------------------------------------------------------------------- data
@@ -146,21 +157,55 @@ def gather_rows(rowptr, colidx, values, n_cols, *, row_idx=None, row_start=0, n_
 
 
 # --------------------------------------------------------------------------- tail kernels
-def colsum(x16, out32, beta=0):
-    _req(x16, torch.bfloat16, "x")
+def _act_t(t, name):
+    """bf16-or-fp32 activation operand"""
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"cellcomm_b200.ops: {name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError(f"cellcomm_b200.ops: {name} must be bf16 or fp32, got {t.dtype}")
+    if t.dim() == 2 and t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"cellcomm_b200.ops: {name} must be row-major (stride(1)==1)")
+
+
+def _mask(*ts):
+    """dtypes bitmask of the C ABI: bit i set when the i-th activation operand is fp32"""
+    m = 0
+    for i, t in enumerate(ts):
+        _act_t(t, f"operand {i}")
+        if t is not None and t.dtype == torch.float32:
+            m |= 1 << i
+    return m
+
+
+def colsum(x, out32, beta=0):
     _req(out32, torch.float32, "out")
-    check(_lib.load().cc_colsum(_p(x16), _ld(x16), x16.shape[0], x16.shape[1], _p(out32), int(beta),
-                                _stream()))
+    check(_lib.load().cc_colsum(_p(x), _ld(x), x.shape[0], x.shape[1], _p(out32), int(beta),
+                                _mask(x), _stream()))
 
 
-def dropout(x16, out16, rate, *, mask=None, seed=0, counter=None, stream_id=0):
-    _req(x16, torch.bfloat16, "x")
-    _req(out16, torch.bfloat16, "out")
+def bias_grad(dy, y, act, out32):
+    """out32[c] = sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient)."""
+    _req(out32, torch.float32, "out")
+    check(_lib.load().cc_bias_grad(_p(dy), _ld(dy), _p(y), _ld(y), dy.shape[0], dy.shape[1],
+                                   int(act), _p(out32), _mask(dy, y), _stream()))
+
+
+def split_bf16(x, hi, lo):
+    """hi + lo ~= x with hi, lo in bf16 (two accumulating GEMM segments)."""
+    _req(hi, torch.bfloat16, "hi")
+    _req(lo, torch.bfloat16, "lo")
+    check(_lib.load().cc_split_bf16(_p(x), _ld(x), _p(hi), _ld(hi), _p(lo), _ld(lo), x.shape[0],
+                                    x.shape[1], _mask(x), _stream()))
+
+
+def dropout(x, out, rate, *, mask=None, seed=0, counter=None, stream_id=0):
     _req(mask, torch.uint8, "mask")
     _req(counter, torch.int64, "counter")
-    check(_lib.load().cc_dropout(_p(x16), _ld(x16), _p(out16), _ld(out16), x16.shape[0],
-                                 x16.shape[1], float(rate), _p(mask), _ld(mask), int(seed),
-                                 _p(counter), int(stream_id), _stream()))
+    check(_lib.load().cc_dropout(_p(x), _ld(x), _p(out), _ld(out), x.shape[0], x.shape[1],
+                                 float(rate), _p(mask), _ld(mask), int(seed), _p(counter),
+                                 int(stream_id), _mask(x, out), _stream()))
 
 
 def dropout_mask(mask, rate, *, seed=0, counter=None, stream_id=0):
@@ -184,102 +229,98 @@ def counter_add(counter, inc=1):
     check(_lib.load().cc_counter_add(_p(counter), int(inc), _stream()))
 
 
-def act_bwd(dy16, y16, dz16, act):
-    check(_lib.load().cc_act_bwd(_p(dy16), _ld(dy16), _p(y16), _ld(y16), _p(dz16), _ld(dz16),
-                                 dy16.shape[0], dy16.shape[1], int(act), _stream()))
+def act_bwd(dy, y, dz, act):
+    check(_lib.load().cc_act_bwd(_p(dy), _ld(dy), _p(y), _ld(y), _p(dz), _ld(dz), dy.shape[0],
+                                 dy.shape[1], int(act), _mask(dy, y, dz), _stream()))
 
 
-def copy2d(src16, dst16, beta=0):
-    _req(src16, torch.bfloat16, "src")
-    _req(dst16, torch.bfloat16, "dst")
-    check(_lib.load().cc_copy2d(_p(src16), _ld(src16), _p(dst16), _ld(dst16), src16.shape[0],
-                                src16.shape[1], int(beta), _stream()))
+def copy2d(src, dst, beta=0, scale=1.0):
+    """dst (+)= scale*src; also the bf16<->fp32 cast."""
+    check(_lib.load().cc_copy2d(_p(src), _ld(src), _p(dst), _ld(dst), src.shape[0], src.shape[1],
+                                int(beta), float(scale), _mask(src, dst), _stream()))
 
 
 def cast_f32_to_bf16(src32, dst16):
-    _req(src32, torch.float32, "src")
-    _req(dst16, torch.bfloat16, "dst")
-    check(_lib.load().cc_cast_f32_to_bf16(_p(src32), _ld(src32), _p(dst16), _ld(dst16),
-                                          src32.shape[0], src32.shape[1], _stream()))
+    copy2d(src32, dst16)
 
 
 def cast_bf16_to_f32(src16, dst32, scale=1.0):
-    _req(src16, torch.bfloat16, "src")
-    _req(dst32, torch.float32, "dst")
-    check(_lib.load().cc_cast_bf16_to_f32(_p(src16), _ld(src16), _p(dst32), _ld(dst32),
-                                          src16.shape[0], src16.shape[1], float(scale), _stream()))
+    copy2d(src16, dst32, scale=scale)
 
 
-def bn_stats(x16, sums):
-    check(_lib.load().cc_bn_stats(_p(x16), _ld(x16), x16.shape[0], x16.shape[1], _p(sums),
+def bn_stats(x, sums):
+    check(_lib.load().cc_bn_stats(_p(x), _ld(x), x.shape[0], x.shape[1], _p(sums), _mask(x),
                                   _stream()))
 
 
-def bn_train_apply(x16, y16, sums, n_total, gamma, beta, eps, momentum, moving_mean, moving_var,
+def bn_train_apply(x, y, sums, n_total, gamma, beta, eps, momentum, moving_mean, moving_var,
                    save_mean, save_rstd):
-    check(_lib.load().cc_bn_train_apply(_p(x16), _ld(x16), _p(y16), _ld(y16), x16.shape[0],
-                                        x16.shape[1], _p(sums), int(n_total), _p(gamma), _p(beta),
-                                        float(eps), float(momentum), _p(moving_mean),
-                                        _p(moving_var), _p(save_mean), _p(save_rstd), _stream()))
+    check(_lib.load().cc_bn_train_apply(_p(x), _ld(x), _p(y), _ld(y), x.shape[0], x.shape[1],
+                                        _p(sums), int(n_total), _p(gamma), _p(beta), float(eps),
+                                        float(momentum), _p(moving_mean), _p(moving_var),
+                                        _p(save_mean), _p(save_rstd), _mask(x, y), _stream()))
 
 
-def bn_infer(x16, y16, gamma, beta, moving_mean, moving_var, eps):
-    check(_lib.load().cc_bn_infer(_p(x16), _ld(x16), _p(y16), _ld(y16), x16.shape[0], x16.shape[1],
-                                  _p(gamma), _p(beta), _p(moving_mean), _p(moving_var), float(eps),
-                                  _stream()))
+def bn_infer(x, y, gamma, beta, moving_mean, moving_var, eps):
+    check(_lib.load().cc_bn_infer(_p(x), _ld(x), _p(y), _ld(y), x.shape[0], x.shape[1], _p(gamma),
+                                  _p(beta), _p(moving_mean), _p(moving_var), float(eps),
+                                  _mask(x, y), _stream()))
 
 
-def bn_bwd_stats(dy16, x16, save_mean, save_rstd, sums2):
-    check(_lib.load().cc_bn_bwd_stats(_p(dy16), _ld(dy16), _p(x16), _ld(x16), dy16.shape[0],
-                                      dy16.shape[1], _p(save_mean), _p(save_rstd), _p(sums2),
+def bn_bwd_stats(dy, x, save_mean, save_rstd, sums2):
+    check(_lib.load().cc_bn_bwd_stats(_p(dy), _ld(dy), _p(x), _ld(x), dy.shape[0], dy.shape[1],
+                                      _p(save_mean), _p(save_rstd), _p(sums2), _mask(dy, x),
                                       _stream()))
 
 
-def bn_bwd_apply(dy16, x16, dx16, gamma, save_mean, save_rstd, sums2, n_total, dgamma=None,
-                 dbeta=None):
-    check(_lib.load().cc_bn_bwd_apply(_p(dy16), _ld(dy16), _p(x16), _ld(x16), _p(dx16), _ld(dx16),
-                                      dy16.shape[0], dy16.shape[1], _p(gamma), _p(save_mean),
-                                      _p(save_rstd), _p(sums2), int(n_total), _p(dgamma),
-                                      _p(dbeta), _stream()))
+def bn_bwd_apply(dy, x, dx, gamma, save_mean, save_rstd, sums2, n_total, dgamma=None, dbeta=None):
+    check(_lib.load().cc_bn_bwd_apply(_p(dy), _ld(dy), _p(x), _ld(x), _p(dx), _ld(dx), dy.shape[0],
+                                      dy.shape[1], _p(gamma), _p(save_mean), _p(save_rstd),
+                                      _p(sums2), int(n_total), _p(dgamma), _p(dbeta),
+                                      _mask(dy, x, dx), _stream()))
 
 
-def bn_infer_bwd(dy16, dx16, gamma, moving_var, eps):
-    check(_lib.load().cc_bn_infer_bwd(_p(dy16), _ld(dy16), _p(dx16), _ld(dx16), dy16.shape[0],
-                                      dy16.shape[1], _p(gamma), _p(moving_var), float(eps),
+def bn_infer_bwd(dy, dx, gamma, moving_var, eps):
+    check(_lib.load().cc_bn_infer_bwd(_p(dy), _ld(dy), _p(dx), _ld(dx), dy.shape[0], dy.shape[1],
+                                      _p(gamma), _p(moving_var), float(eps), _mask(dy, dx),
                                       _stream()))
 
 
-def softmax_fwd(x16, y16=None, y32=None):
-    check(_lib.load().cc_softmax_fwd(_p(x16), _ld(x16), _p(y16), _ld(y16), _p(y32), _ld(y32),
-                                     x16.shape[0], x16.shape[1], _stream()))
+def softmax_fwd(x, y16=None, y32=None):
+    _req(y32, torch.float32, "y32")
+    check(_lib.load().cc_softmax_fwd(_p(x), _ld(x), _p(y16), _ld(y16), _p(y32), _ld(y32),
+                                     x.shape[0], x.shape[1], _mask(x, y16), _stream()))
 
 
-def softmax_bwd(dy16, y16, dx16):
-    check(_lib.load().cc_softmax_bwd(_p(dy16), _ld(dy16), _p(y16), _ld(y16), _p(dx16), _ld(dx16),
-                                     dy16.shape[0], dy16.shape[1], _stream()))
+def softmax_bwd(dy, y, dx):
+    check(_lib.load().cc_softmax_bwd(_p(dy), _ld(dy), _p(y), _ld(y), _p(dx), _ld(dx), dy.shape[0],
+                                     dy.shape[1], _mask(dy, y, dx), _stream()))
 
 
-def bce_fwd_bwd(x32, target, n_total, loss_out, dz16=None, from_logits=True):
+def bce_fwd_bwd(x32, target, n_total, loss_out, dz=None, from_logits=True):
     _req(x32, torch.float32, "x")
     _req(loss_out, torch.float32, "loss_out")
     check(_lib.load().cc_bce_fwd_bwd(_p(x32), _ld(x32), x32.shape[0], int(bool(from_logits)),
-                                     float(target), int(n_total), _p(loss_out), _p(dz16),
-                                     _ld(dz16), _stream()))
+                                     float(target), int(n_total), _p(loss_out), _p(dz), _ld(dz),
+                                     _mask(dz), _stream()))
 
 
-def mse_fwd_bwd(pred16, n_total, loss_out, *, target16=None, target32=None, dpred16=None):
-    check(_lib.load().cc_mse_fwd_bwd(_p(pred16), _ld(pred16), _p(target16), _ld(target16),
-                                     _p(target32), _ld(target32), pred16.shape[0], pred16.shape[1],
-                                     int(n_total), _p(loss_out), _p(dpred16), _ld(dpred16),
-                                     _stream()))
+def mse_fwd_bwd(pred, n_total, loss_out, *, target, dpred=None):
+    _req(loss_out, torch.float32, "loss_out")
+    check(_lib.load().cc_mse_fwd_bwd(_p(pred), _ld(pred), _p(target), _ld(target), pred.shape[0],
+                                     pred.shape[1], int(n_total), _p(loss_out), _p(dpred),
+                                     _ld(dpred), _mask(pred, target, dpred), _stream()))
 
 
-def round_half_even(x16, out16=None, out32=None):
-    check(_lib.load().cc_round_half_even(_p(x16), _ld(x16), _p(out16), _ld(out16), _p(out32),
-                                         _ld(out32), x16.shape[0], x16.shape[1], _stream()))
+def round_half_even(x, out16=None, out32=None):
+    _req(out32, torch.float32, "out32")
+    check(_lib.load().cc_round_half_even(_p(x), _ld(x), _p(out16), _ld(out16), _p(out32),
+                                         _ld(out32), x.shape[0], x.shape[1], _mask(x, out16),
+                                         _stream()))
 
 
 def argmax_onehot(p32, out16=None, out32=None):
+    _req(p32, torch.float32, "p32")
     check(_lib.load().cc_argmax_onehot(_p(p32), _ld(p32), _p(out16), _ld(out16), _p(out32),
                                        _ld(out32), p32.shape[0], p32.shape[1], _stream()))
 

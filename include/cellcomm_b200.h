@@ -84,7 +84,7 @@ int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_dev, const f
  * Model.predict (src/bigan_classify.py:10-75,144-155; src/bigan_cont.py:7-41).
  *
  * D[M,N] = epilogue( sum_s A_s[M,K_s] * B_s[K_s,N] ), bf16 operands, fp32
- * accumulation in tensor memory (tcgen05).  Up to 3 (A_s,B_s) segments
+ * accumulation in tensor memory (tcgen05).  Up to CC_GEMM_MAX_SEG (A_s,B_s) segments
  * accumulate into one tile: that is how Concatenate() is consumed without
  * materialising it.
  *
@@ -102,16 +102,17 @@ int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_dev, const f
  *   if out16:  out16[r,c] = bf16(v + (beta16 ? out16[r,c] : 0))
  */
 enum { CC_ACT_NONE = 0, CC_ACT_SIGMOID = 1, CC_ACT_RELU = 2 };
+#define CC_GEMM_MAX_SEG 4
 
 typedef struct cc_gemm_desc {
   int32_t M, N;
   int32_t a_mn_major, b_mn_major;
   int32_t nseg;
-  const void* a[3];
-  int64_t lda[3];
-  const void* b[3];
-  int64_t ldb[3];
-  int32_t k[3];
+  const void* a[CC_GEMM_MAX_SEG];
+  int64_t lda[CC_GEMM_MAX_SEG];
+  const void* b[CC_GEMM_MAX_SEG];
+  int64_t ldb[CC_GEMM_MAX_SEG];
+  int32_t k[CC_GEMM_MAX_SEG];
   /* epilogue */
   float alpha;
   const float* bias;
@@ -157,20 +158,37 @@ int cc_dense_wgrad(int32_t M, int32_t K, int32_t N, const void* x, int64_t ldx, 
 
 /* --------------------------------------------------------- tail kernels
  * All elementwise / reduction kernels below work on row-major [rows, cols]
- * tensors with explicit ld.  bf16 unless stated.
+ * tensors with explicit ld.  Activation-like operands are bf16 OR fp32: the
+ * trailing `dtypes` bitmask has bit i set when the i-th such operand (in the
+ * order listed beside each function) is fp32.  Activations that feed a
+ * BatchNormalization and all activation gradients are kept in fp32 (1/sigma
+ * amplification and the cancellation in BN backward make bf16 storage too
+ * lossy there, DESIGN.md "precision policy"); GEMM operands are bf16.
  */
 
-/* column sums of a bf16 matrix into fp32: db = sum_rows dZ   (Dense bias grad) */
-int cc_colsum(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* out, int32_t beta,
-              cc_stream_t stream);
+/* column sums into fp32: db = sum_rows dZ (Dense bias grad).  dtypes: x */
+int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out, int32_t beta,
+              int32_t dtypes, cc_stream_t stream);
+
+/* Dense bias gradient from the fp32 upstream gradient: out[c] = sum_r dy[r,c]*act'(y[r,c]).
+ * (Summing the bf16 dZ instead loses the near-cancelling sums of biases that feed a
+ * BatchNormalization.)  dtypes: dy, y */
+int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
+                 int64_t cols, int32_t act, float* out, int32_t dtypes, cc_stream_t stream);
+/* hi = bf16(x), lo = bf16(x - hi): two-term bf16 expansion of an activation, fed to cc_gemm
+ * as two accumulating segments where 8 mantissa bits are too few.  dtypes: x */
+int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo, int64_t ldlo,
+                  int64_t rows, int64_t cols, int32_t dtypes, cc_stream_t stream);
 
 /* Dropout (layers.Dropout, training=True): out = x * keep / (1-rate).
  * mask_u8 != NULL: explicit keep mask (parity tests inject TF's masks this way).
  * mask_u8 == NULL: keep = philox(seed, *counter_dev, stream_id, r, c) >= rate;
- * the same call with the same arguments regenerates the mask in backward. */
-int cc_dropout(const void* x16, int64_t ldx, void* out16, int64_t ldo, int64_t rows, int64_t cols,
+ * the same call with the same arguments regenerates the mask in backward.
+ * dtypes: x, out */
+int cc_dropout(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int64_t cols,
                float rate, const uint8_t* mask_u8, int64_t ldm, uint64_t seed,
-               const uint64_t* counter_dev, uint32_t stream_id, cc_stream_t stream);
+               const uint64_t* counter_dev, uint32_t stream_id, int32_t dtypes,
+               cc_stream_t stream);
 /* write the keep mask the RNG path would use (tests / debugging) */
 int cc_dropout_mask(uint8_t* mask_u8, int64_t ldm, int64_t rows, int64_t cols, float rate,
                     uint64_t seed, const uint64_t* counter_dev, uint32_t stream_id,
@@ -180,54 +198,56 @@ int cc_uniform(float* out32, void* out16, int64_t ld, int64_t rows, int64_t cols
                const uint64_t* counter_dev, uint32_t stream_id, cc_stream_t stream);
 int cc_counter_add(uint64_t* counter_dev, uint64_t inc, cc_stream_t stream);
 
-/* dz = dy * act'(y)  (act: 1 sigmoid, 2 relu), optional accumulate is not needed */
-int cc_act_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy, void* dz16,
-               int64_t lddz, int64_t rows, int64_t cols, int32_t act, cc_stream_t stream);
+/* dz = dy * act'(y)  (act: 0 copy, 1 sigmoid, 2 relu).  dtypes: dy, y, dz */
+int cc_act_bwd(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dz, int64_t lddz,
+               int64_t rows, int64_t cols, int32_t act, int32_t dtypes, cc_stream_t stream);
 
-/* copy a [rows, cols] block (concat materialisation / slicing); beta=1 accumulates */
-int cc_copy2d(const void* src16, int64_t lds, void* dst16, int64_t ldd, int64_t rows,
-              int64_t cols, int32_t beta, cc_stream_t stream);
-int cc_cast_f32_to_bf16(const float* src, int64_t lds, void* dst16, int64_t ldd, int64_t rows,
-                        int64_t cols, cc_stream_t stream);
-int cc_cast_bf16_to_f32(const void* src16, int64_t lds, float* dst, int64_t ldd, int64_t rows,
-                        int64_t cols, float scale, cc_stream_t stream);
+/* dst (+)= scale * src on a [rows, cols] block: concat materialisation, slicing, gradient
+ * accumulation (beta=1) and bf16<->fp32 casts.  dtypes: src, dst */
+int cc_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int64_t cols,
+              int32_t beta, float scale, int32_t dtypes, cc_stream_t stream);
 
 /* BatchNormalization (Keras 2.4 defaults: eps=1e-3, momentum=0.99), SURVEY A.3.
  * stats: sums[0:cols] = sum_r x, sums[cols:2cols] = sum_r x^2 (fp32, overwritten).
- * The caller may all-reduce `sums` across ranks before cc_bn_train_apply. */
-int cc_bn_stats(const void* x16, int64_t ld, int64_t rows, int64_t cols, float* sums,
-                cc_stream_t stream);
+ * The caller may all-reduce `sums` across ranks before cc_bn_train_apply.  dtypes: x */
+int cc_bn_stats(const void* x, int64_t ld, int64_t rows, int64_t cols, float* sums,
+                int32_t dtypes, cc_stream_t stream);
 /* y = gamma*(x-mean)*rstd+beta with batch stats from sums/n_total; writes
  * mean/rstd (fp32, cols each) for backward; updates moving stats:
- * moving = momentum*moving + (1-momentum)*batch (biased variance). */
-int cc_bn_train_apply(const void* x16, int64_t ldx, void* y16, int64_t ldy, int64_t rows,
+ * moving = momentum*moving + (1-momentum)*batch (biased variance).  dtypes: x, y */
+int cc_bn_train_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows,
                       int64_t cols, const float* sums, int64_t n_total, const float* gamma,
                       const float* beta, float eps, float momentum, float* moving_mean,
-                      float* moving_var, float* save_mean, float* save_rstd, cc_stream_t stream);
-/* inference: y = gamma*(x-moving_mean)/sqrt(moving_var+eps)+beta */
-int cc_bn_infer(const void* x16, int64_t ldx, void* y16, int64_t ldy, int64_t rows, int64_t cols,
+                      float* moving_var, float* save_mean, float* save_rstd, int32_t dtypes,
+                      cc_stream_t stream);
+/* inference: y = gamma*(x-moving_mean)/sqrt(moving_var+eps)+beta.  dtypes: x, y */
+int cc_bn_infer(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int64_t cols,
                 const float* gamma, const float* beta, const float* moving_mean,
-                const float* moving_var, float eps, cc_stream_t stream);
-/* backward, training mode.  sums2[0:cols] = sum dy, sums2[cols:2cols] = sum dy*xhat */
-int cc_bn_bwd_stats(const void* dy16, int64_t lddy, const void* x16, int64_t ldx, int64_t rows,
+                const float* moving_var, float eps, int32_t dtypes, cc_stream_t stream);
+/* backward, training mode.  sums2[0:cols] = sum dy, sums2[cols:2cols] = sum dy*xhat.
+ * dtypes: dy, x */
+int cc_bn_bwd_stats(const void* dy, int64_t lddy, const void* x, int64_t ldx, int64_t rows,
                     int64_t cols, const float* save_mean, const float* save_rstd, float* sums2,
-                    cc_stream_t stream);
+                    int32_t dtypes, cc_stream_t stream);
 /* dx = gamma*rstd*(dy - sum_dy/n - xhat*sum_dyxhat/n); dgamma = sum_dyxhat, dbeta = sum_dy
- * (dgamma/dbeta may be NULL when the BN is not being trained) */
-int cc_bn_bwd_apply(const void* dy16, int64_t lddy, const void* x16, int64_t ldx, void* dx16,
+ * (dgamma/dbeta may be NULL when the BN is not being trained; dx may be NULL).
+ * dtypes: dy, x, dx */
+int cc_bn_bwd_apply(const void* dy, int64_t lddy, const void* x, int64_t ldx, void* dx,
                     int64_t lddx, int64_t rows, int64_t cols, const float* gamma,
                     const float* save_mean, const float* save_rstd, const float* sums2,
-                    int64_t n_total, float* dgamma, float* dbeta, cc_stream_t stream);
-/* backward through an inference-mode (frozen) BN: dx = dy*gamma/sqrt(var+eps) */
-int cc_bn_infer_bwd(const void* dy16, int64_t lddy, void* dx16, int64_t lddx, int64_t rows,
-                    int64_t cols, const float* gamma, const float* moving_var, float eps,
+                    int64_t n_total, float* dgamma, float* dbeta, int32_t dtypes,
                     cc_stream_t stream);
+/* backward through an inference-mode (frozen) BN: dx = dy*gamma/sqrt(var+eps).  dtypes: dy, dx */
+int cc_bn_infer_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int64_t rows,
+                    int64_t cols, const float* gamma, const float* moving_var, float eps,
+                    int32_t dtypes, cc_stream_t stream);
 
-/* softmax over the last axis (classify encoder, src/bigan_classify.py:39) */
-int cc_softmax_fwd(const void* x16, int64_t ldx, void* y16, int64_t ldy, float* y32, int64_t ldy32,
-                   int64_t rows, int64_t cols, cc_stream_t stream);
-int cc_softmax_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy, void* dx16,
-                   int64_t lddx, int64_t rows, int64_t cols, cc_stream_t stream);
+/* softmax over the last axis (classify encoder, src/bigan_classify.py:39).  dtypes: x, y */
+int cc_softmax_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, float* y32, int64_t ldy32,
+                   int64_t rows, int64_t cols, int32_t dtypes, cc_stream_t stream);
+/* dtypes: dy, y, dx */
+int cc_softmax_bwd(const void* dy, int64_t lddy, const void* y, int64_t ldy, void* dx,
+                   int64_t lddx, int64_t rows, int64_t cols, int32_t dtypes, cc_stream_t stream);
 
 /* losses.binary_crossentropy on the (rows,1) discriminator output against a
  * constant target (0.95 / 0: src/bigan_classify.py:128-129).  Keras 2.4 uses the
@@ -235,19 +255,22 @@ int cc_softmax_bwd(const void* dy16, int64_t lddy, const void* y16, int64_t ldy,
  * input is the PRE-activation (from_logits=1); from_logits=0 takes probabilities
  * and clips them to [1e-7, 1-1e-7] (Keras backend epsilon).
  * loss_out[0] += sum_r bce_r / n_total;  dz = dLoss/dlogit = (sigmoid(x)-t)/n_total
- * (bf16, may be NULL).  n_total is the GLOBAL batch so sharded batches sum to the
- * global mean. */
+ * (may be NULL).  n_total is the GLOBAL batch so sharded batches sum to the
+ * global mean.  dtypes: dz */
 int cc_bce_fwd_bwd(const float* x32, int64_t ldx, int64_t rows, int32_t from_logits, float target,
-                   int64_t n_total, float* loss_out, void* dz16, int64_t lddz, cc_stream_t stream);
-/* losses.mse: mean over all rows*cols elements; dpred = 2*(pred-target)/(n_total*cols) */
-int cc_mse_fwd_bwd(const void* pred16, int64_t ldp, const void* target16, int64_t ldt,
-                   const float* target32, int64_t ldt32, int64_t rows, int64_t cols,
-                   int64_t n_total, float* loss_out, void* dpred16, int64_t lddp,
+                   int64_t n_total, float* loss_out, void* dz, int64_t lddz, int32_t dtypes,
                    cc_stream_t stream);
+/* losses.mse: mean over all rows*cols elements; dpred = 2*(pred-target)/(n_total*cols)
+ * (may be NULL).  dtypes: pred, target, dpred */
+int cc_mse_fwd_bwd(const void* pred, int64_t ldp, const void* target, int64_t ldt, int64_t rows,
+                   int64_t cols, int64_t n_total, float* loss_out, void* dpred, int64_t lddp,
+                   int32_t dtypes, cc_stream_t stream);
 
 /* tf.math.round (half to even) for generate_cells, src/bigan_basic.py:40-44 */
-int cc_round_half_even(const void* x16, int64_t ldx, void* out16, int64_t ldo, float* out32,
-                       int64_t ldo32, int64_t rows, int64_t cols, cc_stream_t stream);
+/* dtypes: x, out */
+int cc_round_half_even(const void* x, int64_t ldx, void* out, int64_t ldo, float* out32,
+                       int64_t ldo32, int64_t rows, int64_t cols, int32_t dtypes,
+                       cc_stream_t stream);
 /* to_categorical(argmax(p,-1)): src/bigan_classify.py:121-124 */
 int cc_argmax_onehot(const float* p32, int64_t ldp, void* out16, int64_t ldo, float* out32,
                      int64_t ldo32, int64_t rows, int64_t cols, cc_stream_t stream);

@@ -381,39 +381,47 @@ class OracleBiGan:
             ctxs[trained].commit_bn()
         return float(loss.detach())
 
+    def substep(self, k, x, z, r, masks=None):
+        """Sub-step k (1..8) of trainings_step; returns the loss for the six updates."""
+        B = x.shape[0]
+        mk = lambda s: self._masks_for(s, B, masks)
+        if k == 1:   # _train_gen_w_discr: BCE(D(z, G(z,r)), 0.95), updates G          :145
+            return self._update("1", "G", lambda c: bce_from_logits(
+                self._D(c("D"), z, self._G(c("G"), z, r), logits=True), REAL_LABEL), mk(1))
+        if k == 2:   # _train_gen_w_enc: MSE(G(E(x), r), x), updates G                  :146
+            return self._update("2", "G", lambda c: mse(
+                self._G(c("G"), self._E(c("E"), x), r), x), mk(2))
+        if k == 3:   # _train_enc_w_discr: BCE(D(E(x), x), 0), updates E                :150
+            return self._update("3", "E", lambda c: bce_from_logits(
+                self._D(c("D"), self._E(c("E"), x), x, logits=True), 0.0), mk(3))
+        if k == 4:   # _train_enc_w_gen: MSE(E(G(z,r)), z), updates E                   :151
+            return self._update("4", "E", lambda c: mse(
+                self._E(c("E"), self._G(c("G"), z, r)), z), mk(4))
+        if k == 5:   # generated_cells = round(G.predict((z, r)))                       :136
+            self.gen_cells = self.generate_cells(z, r)
+            return None
+        if k == 6:   # D.train_on_batch((z, generated_cells), zeros)                    :137
+            return self._update("6", "D", lambda c: bce_from_logits(
+                self._D(c("D"), z, self.gen_cells, logits=True), 0.0), mk(6))
+        if k == 7:   # generated_encodings = trainings_encoding_prediction(batch)       :138
+            self.gen_enc = self.trainings_encoding_prediction(x)
+            return None
+        if k == 8:   # D.train_on_batch((generated_encodings, batch), 0.95)             :139
+            return self._update("8", "D", lambda c: bce_from_logits(
+                self._D(c("D"), self.gen_enc, x, logits=True), REAL_LABEL), mk(8))
+        raise ValueError(k)
+
     def trainings_step(self, batch, encodings, noise, masks=None):
         """src/bigan_classify.py:126-155.  masks: {substep: {net: [keep masks in call order]}}
-        for substeps 1,2,3,4,6,8; None or missing entries => all-ones (dropout rate still
-        rescales: pass explicit ones to mimic 'no unit dropped')."""
+        for substeps 1,2,3,4,6,8; missing entries => all-ones masks (nothing dropped, the
+        1/(1-rate) rescale still applies)."""
         x = self.t(batch)
         z = self.t(encodings)
         r = self.t(noise)
-        B = x.shape[0]
-        mk = lambda s: self._masks_for(s, B, masks)
-
-        # (1) _train_gen_w_discr: BCE(D(z, G(z,r)), 0.95), updates G          :145
-        l1 = self._update("1", "G", lambda c: bce_from_logits(
-            self._D(c("D"), z, self._G(c("G"), z, r), logits=True), REAL_LABEL), mk(1))
-        # (2) _train_gen_w_enc: MSE(G(E(x), r), x), updates G                  :146
-        l2 = self._update("2", "G", lambda c: mse(self._G(c("G"), self._E(c("E"), x), r), x), mk(2))
-        # (3) _train_enc_w_discr: BCE(D(E(x), x), 0), updates E                :150
-        l3 = self._update("3", "E", lambda c: bce_from_logits(
-            self._D(c("D"), self._E(c("E"), x), x, logits=True), 0.0), mk(3))
-        # (4) _train_enc_w_gen: MSE(E(G(z,r)), z), updates E                   :151
-        l4 = self._update("4", "E", lambda c: mse(self._E(c("E"), self._G(c("G"), z, r)), z), mk(4))
-        # (5) generated_cells = round(G.predict((z, r)))                       :136
-        gen_cells = self.generate_cells(z, r)
-        # (6) D.train_on_batch((z, generated_cells), zeros)                    :137
-        l6 = self._update("6", "D", lambda c: bce_from_logits(
-            self._D(c("D"), z, gen_cells, logits=True), 0.0), mk(6))
-        # (7) generated_encodings = trainings_encoding_prediction(batch)       :138
-        gen_enc = self.trainings_encoding_prediction(x)
-        # (8) D.train_on_batch((generated_encodings, batch), 0.95)             :139
-        l8 = self._update("8", "D", lambda c: bce_from_logits(
-            self._D(c("D"), gen_enc, x, logits=True), REAL_LABEL), mk(8))
-        self.last_losses = {"1": l1, "2": l2, "3": l3, "4": l4, "6": l6, "8": l8}
-        self.last_aux = {"generated_cells": gen_cells, "generated_encodings": gen_enc}
-        return l1 + l2, l3 + l4, float(np.mean([l6, l8]))
+        l = {k: self.substep(k, x, z, r, masks) for k in (1, 2, 3, 4, 5, 6, 7, 8)}
+        self.last_losses = {str(k): l[k] for k in (1, 2, 3, 4, 6, 8)}
+        self.last_aux = {"generated_cells": self.gen_cells, "generated_encodings": self.gen_enc}
+        return l[1] + l[2], l[3] + l[4], float(np.mean([l[6], l[8]]))
 
     def _masks_for(self, substep, B, masks):
         nets = {1: ("G", "D"), 2: ("E", "G"), 3: ("E", "D"), 4: ("G", "E"), 6: ("D",), 8: ("D",)}
@@ -434,6 +442,14 @@ class OracleBiGan:
             keys = ("kernel", "bias") if l["kind"] == "dense" else (
                 "gamma", "beta", "moving_mean", "moving_var")
             out += [l[k].detach().clone() for k in keys]
+        return out
+
+    def get_slots(self, net):
+        """[(ms, mom)] per trainable tensor, creation order (zeros before the first update)."""
+        out = []
+        for p in trainable_params(self.nets()[net]):
+            ms, mom = self.slots.get(id(p), (torch.zeros_like(p), torch.zeros_like(p)))
+            out.append((ms.clone(), mom.clone()))
         return out
 
     def set_weights(self, net, arrays):

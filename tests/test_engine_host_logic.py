@@ -1,0 +1,120 @@
+"""Host logic of cellcomm_b200.engine (graph wiring, freeze pattern, gradient routing, RMSprop
+bookkeeping) against the oracle, with the kernels replaced by tests/ops_emulator.py.
+
+CPU-only (`-m "not gpu"`).  The real kernels are checked on the GPU in test_parity_gpu.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigan_oracle as O
+
+import ops_emulator
+from cellcomm_b200 import engine as eng
+
+
+@pytest.fixture(autouse=True)
+def _emulated_ops(monkeypatch):
+    monkeypatch.setattr(eng, "ops", ops_emulator)
+    yield
+
+
+def _pair(variant, Z, G, B, seed=0):
+    orc = O.OracleBiGan(variant, Z, G, seed=seed, dtype=torch.float64)
+    e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cpu", seed=seed)
+    for n in ("G", "E", "D"):
+        e.nets[n].set_weights([w.numpy() for w in orc.get_weights(n)])
+    return orc, e
+
+
+def _inputs(variant, Z, G, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.poisson(torch.rand(B, G, generator=g) * 3, generator=g)
+    if variant == "cont":
+        z = torch.rand(B, Z, generator=g)
+    else:
+        z = torch.nn.functional.one_hot(torch.randint(0, Z, (B,), generator=g), Z).float()
+    r = torch.rand(B, Z, generator=g)
+    return x, z, r
+
+
+def _close(a, b, rtol=2e-4, atol=2e-6, what=""):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    assert np.all(err <= tol), f"{what}: max err {err.max():.3e} (ref max {np.abs(b).max():.3e})"
+
+
+@pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 200, 16), ("classify", 4, 60, 12),
+                                           ("cont", 8, 5, 3)])
+def test_trainings_step_matches_oracle(variant, Z, G, B):
+    orc, e = _pair(variant, Z, G, B)
+    for step in range(2):
+        x, z, r = _inputs(variant, Z, G, B, 100 + step)
+        masks = O.make_masks(variant, Z, G, B, 7 + step)
+        ref = orc.trainings_step(x, z, r, masks)
+        e.set_latents(z, r, B)
+        x16 = ops_emulator.alloc2d(B, G)
+        x16.copy_(x)
+        got = e.train_step(x16, masks)
+        _close([float(v) for v in got], ref, rtol=1e-4, what=f"losses step {step}")
+        six = e.last_losses[:6].tolist()
+        _close(six, [orc.last_losses[k] for k in ("1", "2", "3", "4", "6", "8")], rtol=1e-4,
+               what="per-substep losses")
+        # gradients of the LAST update of each net (G: sub-step 2, E: 4, D: 8)
+        for net, sub in (("G", "2"), ("E", "4"), ("D", "8")):
+            n = e.nets[net]
+            got_g = []
+            for L in n.layers:
+                got_g += [L["dw"], L["db"]] if L["kind"] == "dense" else [L["dgamma"], L["dbeta"]]
+            for i, (a, b) in enumerate(zip(got_g, orc.last_grads[sub])):
+                if b.numel() == 0:
+                    assert a.numel() == 0
+                    continue
+                scale = float(b.abs().max()) + 1e-12
+                _close(a.numpy() / scale, b.numpy() / scale, rtol=2e-3, atol=3e-4,
+                       what=f"{net} grad {i} step {step}")
+        # post-step weights, BN moving statistics
+        for net in ("G", "E", "D"):
+            for i, (a, b) in enumerate(zip(e.nets[net].get_weights(), orc.get_weights(net))):
+                _close(a, b.numpy(), rtol=1e-3, atol=1e-4, what=f"{net} weight {i} step {step}")
+
+
+def test_predict_paths_match_oracle():
+    variant, Z, G, B = "cont", 3, 120, 10
+    orc, e = _pair(variant, Z, G, B)
+    x, z, r = _inputs(variant, Z, G, B, 5)
+    x16 = ops_emulator.alloc2d(B, G)
+    x16.copy_(x)
+    out32 = torch.zeros(B, Z)
+    e.encode(x16, out32=out32)
+    _close(out32.numpy(), orc.encoding_prediction(x).numpy(), what="encode")
+    e.set_latents(z, r, B)
+    g32 = torch.zeros(B, G)
+    e.generate(B, out32=g32)
+    _close(g32.numpy(), orc.generator_predict(z, r).numpy(), what="generate")
+    p = torch.zeros(B, 1)
+    e.discriminate(e.z32[:B], x16, p)
+    _close(p.numpy(), orc.discriminator_predict(z, x).numpy(), what="discriminate")
+
+
+def test_rng_dropout_mode_runs_and_advances_counter():
+    e = eng.BiGanEngine("cont", 3, 64, max_batch=8, device="cpu", seed=1)
+    x16 = ops_emulator.alloc2d(8, 64)
+    x16.copy_(torch.rand(8, 64).round())
+    e.draw_latents(8)
+    g, ee, d = e.train_step(x16)
+    assert all(np.isfinite(float(v)) for v in (g, ee, d))
+    assert int(e.rng_counter.item()) == 1
+
+
+def test_loss_scalar_behaves_like_a_float():
+    a = eng.LossScalar(torch.tensor(1.5))
+    acc = 0
+    acc += a
+    acc += a
+    assert float(acc) == 3.0
+    assert f"{acc:6.3f}" == " 3.000"
+    assert float(sum((a, a, a))) == 4.5

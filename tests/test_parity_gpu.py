@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on identical weights,
+minibatches, priors and dropout masks.
+
+Stated tolerances (north_star: "rel. 1e-2 on losses, cosine >= 0.999 on encodings"; bf16 GEMM
+operands with fp32 accumulation vs the oracle's fp32):
+
+    losses            |got - ref| <= 1e-2 * |ref| + 1e-3          (every sub-step and g/e/d)
+    encodings         per-cell cosine >= 0.999 and max abs err <= 2e-2
+    gradients         from IDENTICAL weights (state synchronised from the oracle before every
+                      sub-step): whole-network flat gradient cosine >= 0.98; every parameter
+                      tensor that carries >= 2 % of the network's gradient norm: cosine >= 0.95
+                      (default precision level CELLCOMM_B200_SPLIT=1; level 3 reaches 0.99 /
+                      0.985, see tests/test_precision_budget.py and DESIGN.md)
+    updated weights   max |dw_got - dw_ref| <= 5 % of the largest RMSprop step of that tensor
+
+Why gradients are compared per sub-step from synchronised weights: RMSprop's first step moves
+every weight by ~lr/sqrt(1-rho) = 0.019 whatever the gradient's size, which is larger than the
+weights themselves (glorot limit 0.013 on the wide layers), so a 1 % gradient difference in
+sub-step 1 becomes a ~2 % weight difference for sub-step 2.  The free-running step is still
+compared end to end on its losses.  tests/test_precision_budget.py reproduces these numbers on
+the CPU by emulating bf16 storage.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+UPDATES = {1: "G", 2: "G", 3: "E", 4: "E", 6: "D", 8: "D"}
+
+
+def _cos(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    na, nb = np.linalg.norm(a), np.linalg.norm(b)
+    if nb < 1e-30 or na < 1e-30:
+        return 1.0 if abs(na - nb) < 1e-12 else 0.0
+    return float(a @ b / (na * nb))
+
+
+def _setup(variant, Z, G, B, seed=0):
+    from cellcomm_b200 import engine as eng
+    orc = O.OracleBiGan(variant, Z, G, seed=seed, dtype=torch.float32)
+    e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cuda", seed=seed)
+    _sync(orc, e)
+    return orc, e
+
+
+def _sync(orc, e):
+    for n in ("G", "E", "D"):
+        e.nets[n].set_weights([w.numpy() for w in orc.get_weights(n)])
+        e.nets[n].set_slots([(a.numpy(), b.numpy()) for a, b in orc.get_slots(n)])
+
+
+def _inputs(variant, Z, G, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    # 10x-like counts: ~6 % dense, small counts, 1 % of entries x50 (beyond bf16's exact range)
+    dense = torch.rand(B, G, generator=g) < 0.06
+    cnt = torch.poisson(torch.full((B, G), 1.2), generator=g) + 1
+    big = torch.rand(B, G, generator=g) < 0.01
+    x = dense.float() * cnt * (1 + 49 * big.float())
+    if variant == "cont":
+        z = torch.rand(B, Z, generator=g)
+    else:
+        z = torch.nn.functional.one_hot(torch.randint(0, Z, (B,), generator=g), Z).float()
+    r = torch.rand(B, Z, generator=g)
+    return x, z, r
+
+
+def _dev_masks(masks):
+    return {s: {n: [m.cuda() for m in ms] for n, ms in d.items()} for s, d in masks.items()}
+
+
+def _grads(net):
+    out = []
+    for L in net.layers:
+        out += [L["dw"], L["db"]] if L["kind"] == "dense" else [L["dgamma"], L["dbeta"]]
+    return [t.detach().float().cpu().numpy() for t in out]
+
+
+@pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 2000, 128), ("classify", 10, 600, 64),
+                                           ("cont", 8, 5, 3), ("cont", 3, 333, 7)])
+def test_every_substep_from_identical_weights(variant, Z, G, B):
+    from cellcomm_b200 import ops
+    orc, e = _setup(variant, Z, G, B)
+    x, z, r = _inputs(variant, Z, G, B, 11)
+    masks = O.make_masks(variant, Z, G, B, 3)
+    dmasks = _dev_masks(masks)
+    x16 = ops.alloc2d(B, G)
+    x16.copy_(x)
+    e.set_latents(z, r, B)
+    xo, zo, ro = orc.t(x), orc.t(z), orc.t(r)
+    ops.fill_f32(e.loss_buf, 0.0)
+    slot = {1: 0, 2: 1, 3: 2, 4: 3, 6: 4, 8: 5}
+    for k in (1, 2, 3, 4, 5, 6, 7, 8):
+        _sync(orc, e)
+        if k == 6:   # same generated cells on both sides (rounding flips are input noise)
+            e.gen_cells[:B].copy_(orc.gen_cells)
+        if k == 8:
+            e.gen_enc32[:B].copy_(orc.gen_enc)
+        before = {n: orc.get_weights(n) for n in ("G", "E", "D")}
+        ref_loss = orc.substep(k, xo, zo, ro, masks)
+        e.substep(k, x16, dmasks)
+        torch.cuda.synchronize()
+        if k not in UPDATES:
+            continue
+        got_loss = float(e.loss_buf[slot[k]])
+        assert abs(got_loss - ref_loss) <= 1e-2 * abs(ref_loss) + 1e-3, \
+            f"sub-step {k}: loss {got_loss} vs {ref_loss}"
+        net = UPDATES[k]
+        got, ref = _grads(e.nets[net]), [g.numpy() for g in orc.last_grads[str(k)]]
+        flat_g = np.concatenate([a.ravel() for a in got]) if got else np.zeros(0)
+        flat_r = np.concatenate([a.ravel() for a in ref]) if ref else np.zeros(0)
+        assert _cos(flat_g, flat_r) >= 0.98, f"sub-step {k} {net}: flat cosine {_cos(flat_g, flat_r)}"
+        total = np.linalg.norm(flat_r)
+        for i, (a, b) in enumerate(zip(got, ref)):
+            if b.size == 0 or np.linalg.norm(b) < 2e-2 * total:
+                continue       # near-zero tensors (biases in front of a BN): flat cosine only
+            c = _cos(a, b)
+            assert c >= 0.95, f"sub-step {k} {net} grad tensor {i}: cosine {c}"
+        # the RMSprop update itself, from identical weights and slots
+        after_ref = orc.get_weights(net)
+        after_got = e.nets[net].get_weights()
+        for i, (w0, w1, wg) in enumerate(zip(before[net], after_ref, after_got)):
+            if w0.numel() == 0:
+                continue
+            step = (w1 - w0).abs().max().item()
+            err = np.abs(wg - w1.numpy()).max()
+            assert err <= 0.05 * step + 1e-6, f"sub-step {k} {net} tensor {i}: {err} vs step {step}"
+
+
+@pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 2000, 128), ("classify", 10, 600, 64)])
+def test_free_running_step_losses(variant, Z, G, B):
+    """The whole trainings_step without re-synchronisation: the three returned losses."""
+    from cellcomm_b200 import ops
+    orc, e = _setup(variant, Z, G, B)
+    x, z, r = _inputs(variant, Z, G, B, 11)
+    masks = O.make_masks(variant, Z, G, B, 3)
+    ref = orc.trainings_step(x, z, r, masks)
+    x16 = ops.alloc2d(B, G)
+    x16.copy_(x)
+    e.set_latents(z, r, B)
+    got = e.train_step(x16, _dev_masks(masks))
+    torch.cuda.synchronize()
+    six_ref = [orc.last_losses[k] for k in ("1", "2", "3", "4", "6", "8")]
+    for name, a, b in zip("123468", e.last_losses[:6].tolist(), six_ref):
+        assert abs(a - b) <= 1e-2 * abs(b) + 1e-3, f"sub-step {name} loss {a} vs {b}"
+    for a, b in zip(got, ref):
+        assert abs(float(a) - b) <= 1e-2 * abs(b) + 2e-3
+
+
+def test_encodings_and_generated_cells():
+    from cellcomm_b200 import ops
+    variant, Z, G, B = "cont", 3, 3000, 200
+    orc, e = _setup(variant, Z, G, B, seed=4)
+    x, z, r = _inputs(variant, Z, G, B, 21)
+    x16 = ops.alloc2d(B, G)
+    x16.copy_(x)
+    out = torch.empty(B, Z, device="cuda")
+    e.encode(x16, out32=out)
+    ref = orc.encoding_prediction(x).numpy()
+    got = out.cpu().numpy()
+    for i in range(B):
+        assert _cos(got[i], ref[i]) >= 0.999
+    assert np.abs(got - ref).max() <= 2e-2
+    e.set_latents(z, r, B)
+    g32 = torch.empty(B, G, device="cuda")
+    e.generate(B, out32=g32)
+    refg = orc.generator_predict(z, r).numpy()
+    assert _cos(g32.cpu().numpy(), refg) >= 0.999
+    p = torch.empty(B, 1, device="cuda")
+    e.discriminate(e.z32[:B], x16, p)
+    refp = orc.discriminator_predict(z, x).numpy()
+    assert np.abs(p.cpu().numpy() - refp).max() <= 2e-2
+
+
+def test_three_steps_track_the_oracle():
+    from cellcomm_b200 import ops
+    variant, Z, G, B = "cont", 3, 1200, 64
+    orc, e = _setup(variant, Z, G, B, seed=2)
+    for step in range(3):
+        x, z, r = _inputs(variant, Z, G, B, 30 + step)
+        masks = O.make_masks(variant, Z, G, B, 40 + step)
+        ref = orc.trainings_step(x, z, r, masks)
+        x16 = ops.alloc2d(B, G)
+        x16.copy_(x)
+        e.set_latents(z, r, B)
+        got = e.train_step(x16, _dev_masks(masks))
+        for a, b in zip(got, ref):
+            # later steps inherit the first steps' weight differences (see module docstring)
+            assert abs(float(a) - b) <= 5e-2 * abs(b) + 5e-3, f"step {step}: {float(a)} vs {b}"
+
+
+def test_rng_mode_trains():
+    """production mode: priors and dropout masks from the device Philox streams"""
+    from cellcomm_b200 import engine as eng, ops
+    B, G = 128, 1500
+    e = eng.BiGanEngine("cont", 3, G, max_batch=B, device="cuda", seed=0)
+    x, _, _ = _inputs("cont", 3, G, B, 1)
+    x16 = ops.alloc2d(B, G)
+    x16.copy_(x)
+    losses = []
+    for _ in range(3):
+        e.draw_latents(B)
+        g, ee, d = e.train_step(x16)
+        losses.append((float(g), float(ee), float(d)))
+    assert all(np.isfinite(v) for t in losses for v in t)
+    assert int(e.rng_counter.item()) == 3

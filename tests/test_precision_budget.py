@@ -1,0 +1,71 @@
+"""Numerics budget of the bf16 path, measured on the CPU by emulating the GPU's storage
+precision (tests/ops_emulator.py with COMPUTE_DTYPE = bfloat16: every tensor the CUDA path
+keeps in bf16 is rounded to bf16 here, GEMMs accumulate exactly).  Same protocol as
+tests/test_parity_gpu.py::test_every_substep_from_identical_weights, so the stated gradient
+tolerances are reproducible without a GPU, for the default precision level (auto) and
+the precise one (3).  With the bf16 weight copy replaced by fp32 every cosine is 1.0000: the
+residual is rounding of the GEMM operands, not an algorithmic difference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bigan_oracle as O
+
+import ops_emulator
+from cellcomm_b200 import engine as eng
+
+import test_parity_gpu as P
+
+
+def _run(monkeypatch, level, small_width, weights_dtype=torch.bfloat16):
+    monkeypatch.setattr(eng, "ops", ops_emulator)
+    monkeypatch.setattr(eng, "_SPLIT_PRECISION", level)
+    monkeypatch.setattr(eng, "_SMALL_WIDTH", small_width)
+    variant, Z, G, B = "cont", 3, 3000, 96
+    orc = O.OracleBiGan(variant, Z, G, seed=0, dtype=torch.float32)
+    monkeypatch.setattr(ops_emulator, "COMPUTE_DTYPE", weights_dtype)
+    e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cpu", seed=0)
+    monkeypatch.setattr(ops_emulator, "COMPUTE_DTYPE", torch.bfloat16)
+    x, z, r = P._inputs(variant, Z, G, B, 11)
+    masks = O.make_masks(variant, Z, G, B, 3)
+    x16 = ops_emulator.alloc2d(B, G)
+    x16.copy_(x)
+    e.set_latents(z, r, B)
+    xo, zo, ro = orc.t(x), orc.t(z), orc.t(r)
+    flat, worst = {}, {}
+    for k in (1, 2, 3, 4, 5, 6, 7, 8):
+        P._sync(orc, e)
+        if k == 6:
+            e.gen_cells[:B].copy_(orc.gen_cells)
+        if k == 8:
+            e.gen_enc32[:B].copy_(orc.gen_enc)
+        orc.substep(k, xo, zo, ro, masks)
+        e.substep(k, x16, masks)
+        if k not in P.UPDATES:
+            continue
+        got = P._grads(e.nets[P.UPDATES[k]])
+        ref = [g.numpy() for g in orc.last_grads[str(k)]]
+        flat_g = np.concatenate([a.ravel() for a in got])
+        flat_r = np.concatenate([a.ravel() for a in ref])
+        flat[k] = P._cos(flat_g, flat_r)
+        total = np.linalg.norm(flat_r)
+        worst[k] = min(P._cos(a, b) for a, b in zip(got, ref)
+                       if np.linalg.norm(b) >= 2e-2 * total)
+    return flat, worst
+
+
+# small_width=256 makes this reduced network's 300..900-wide layers count as "wide", like the
+# 1684..10108-wide layers of the 33,694-gene configuration
+def test_default_precision_level(monkeypatch):
+    flat, worst = _run(monkeypatch, None, 256)       # "auto": G at level 3, E and D at level 1
+    print("auto: flat", flat, "worst tensor", worst)
+    assert min(flat.values()) >= 0.98
+    assert min(worst.values()) >= 0.95
+
+
+def test_residual_is_weight_rounding_only(monkeypatch):
+    """fp32 compute copy of the weights, everything else as on the GPU: cosine 1.0000"""
+    flat, worst = _run(monkeypatch, 3, 256, weights_dtype=torch.float32)
+    assert min(flat.values()) >= 0.9999
+    assert min(worst.values()) >= 0.9995
