@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): BiGAN train cells/sec and encode cells/sec on
+synthetic 10x-shaped data, 30,000 cells x 33,694 genes, ContinuousCellBiGan, Z = 3.
+
+    python bench.py --gpus N --steps K --warmup W [--batch B] [--impl reference]
+
+One "step" = one `trainings_step` (six RMSprop updates + two predicts, reference
+src/bigan_classify.py:126-155) on one batch of B cells per GPU.  Prints ONE JSON line.
+
+  value     whole-job train cells/s with inputs resident in HBM (device CSR, device index and
+            prior buffers), CUDA-event timed, max over ranks
+  e2e       the same metric through the reference-facing Python API
+            (`CellTraining.sample_cell_data` + `network.trainings_step`): host sampling,
+            host->device copy of the batch indices and priors, device->host read of the losses
+  roofline  dominant kernel (the tcgen05 GEMM family): algorithmic FLOPs of the step /
+            summed GEMM kernel time, against the measured dense bf16 peak
+  cpu_baseline / --impl reference   the oracle (torch-CPU restatement of the reference; TensorFlow
+            is not installable here) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENES, CELLS, Z = 33694, 30000, 3
+FLOP_PER_CELL_TRAIN = 13.237e9      # SURVEY.md App. B (dense-equivalent 2*M*N*K, Continuous)
+FLOP_PER_CELL_ENCODE = 0.3524e9
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+                "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------ data
+def synth_csr(n_cells, n_genes, seed, device):
+    """10x-shaped synthetic counts as a CSR: nnz/cell ~
+    clip(lognormal(ln 2000, 0.35), 200, 8000), Zipf-like gene popularity, counts
+    1 + geometric(0.45), 1 % of entries x50; every gene gets >= 1 non-zero so the pivoted
+    gene_size equals n_genes.  Built on the device (data synthesis is not timed)."""
+    import numpy as np
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    nnz_row = np.clip(np.round(rng.lognormal(np.log(2000.0), 0.35, n_cells)), 200,
+                      min(8000, n_genes)).astype(np.int64)
+    logp = -0.9 * torch.log(torch.arange(1, n_genes + 1, device=device, dtype=torch.float32))
+    logp = logp[torch.randperm(n_genes, generator=g, device=device)]
+    rowptr = np.zeros(n_cells + 1, dtype=np.int64)
+    np.cumsum(nnz_row, out=rowptr[1:])
+    colidx = torch.empty(int(rowptr[-1]), dtype=torch.int32, device=device)
+    kmax = int(nnz_row.max())
+    chunk = 2048
+    for s in range(0, n_cells, chunk):
+        e = min(n_cells, s + chunk)
+        u = torch.rand((e - s, n_genes), generator=g, device=device)
+        keys = logp - torch.log(-torch.log(u.clamp_min(1e-20)))       # Gumbel top-k sampling
+        # force gene j into cell j % n_cells so that no gene id is absent
+        rows = torch.arange(s, e, device=device)
+        for rep in range((n_genes + n_cells - 1) // n_cells):
+            forced = rows + rep * n_cells
+            ok = forced < n_genes
+            keys[ok, forced[ok]] = float("inf")
+        top = torch.topk(keys, kmax, dim=1).indices
+        for i in range(e - s):
+            k = int(nnz_row[s + i])
+            colidx[rowptr[s + i]:rowptr[s + i] + k] = torch.sort(top[i, :k]).values.to(torch.int32)
+    nnz = int(rowptr[-1])
+    geo = torch.floor(torch.log(torch.rand(nnz, generator=g, device=device).clamp_min(1e-20)) /
+                      float(np.log(1 - 0.45)))
+    vals = 1.0 + geo
+    big = torch.rand(nnz, generator=g, device=device) < 0.01
+    vals = torch.where(big, vals * 50.0, vals)
+    return rowptr, colidx.cpu().numpy(), vals.cpu().numpy().astype(np.float64)
+
+
+def make_matrix(n_cells, n_genes, seed, device):
+    import numpy as np
+    from cellcomm_b200.cell_type_training import CellMatrix
+    rowptr, colidx, vals = synth_csr(n_cells, n_genes, seed, device)
+    return CellMatrix(rowptr, colidx, vals, np.arange(1, n_cells + 1), np.arange(1, n_genes + 1))
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def oracle_step_rate(batch, steps, warmup, genes, note):
+    """cells/s of the oracle's trainings_step on the host cores (all threads)."""
+    import torch
+    from oracle import bigan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = O.OracleBiGan("cont", Z, genes, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(batch, genes, generator=g) < 0.06).float() * \
+        (torch.poisson(torch.full((batch, genes), 1.2), generator=g) + 1)
+    masks = O.make_masks("cont", Z, genes, batch, 1)
+    times = []
+    for i in range(warmup + steps):
+        z, r = torch.rand(batch, Z, generator=g), torch.rand(batch, Z, generator=g)
+        t0 = time.perf_counter()
+        m.trainings_step(x, z, r, masks)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"value": batch / dt, "unit": "cells/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{steps} trainings_step(s) of {batch} cells x {genes} genes, {note}; "
+                      f"oracle = torch-CPU fp32 restatement of the reference's Keras step "
+                      f"(TensorFlow 2.4 is not installable here)",
+            "sec_per_step": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  TensorFlow/Keras is
+    not installed and cannot be (no network), so this times the oracle port on the host cores,
+    rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    res = oracle_step_rate(batch, max(1, args.steps), max(0, args.warmup), args.genes,
+                           "same synthetic count model as the GPU arm")
+    line = {
+        "impl": "reference", "metric": "BiGAN train cells/sec", "value": res["value"],
+        "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"ContinuousCellBiGan trainings_step on synthetic 10x-shaped matrix "
+                        f"{args.cells} cells x {args.genes} genes (BASELINE.json configs[1])",
+            "cells": args.cells, "genes": args.genes, "encoding_size": Z,
+            "batch_per_gpu": batch, "l2_policy": "inputs larger than L2 (0.9-1.8 GB of bf16 "
+            "weights streamed per update; every weight is rewritten between uses)"}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cellcomm_b200 import engine as eng, ops
+    from cellcomm_b200.cell_type_training import CellTraining
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_setup = time.time()
+    data = make_matrix(args.cells, args.genes, 20260101, dev)
+    assert data.shape == (args.cells, args.genes)
+    np.random.seed(1000 + rank)          # each rank samples its own cells (weak scaling)
+    trainer = CellTraining(data, batch_size=B, encoding_size=Z)
+    net = trainer.network
+    e = net._engine
+    rowptr, colidx, values = data.device_csr(dev)
+    setup_s = time.time() - t_setup
+
+    # ---- device-resident loop: indices + priors already in HBM
+    n_pre = args.warmup + args.steps
+    idx_all = torch.stack([torch.from_numpy(np.random.permutation(args.cells)[:B])
+                           for _ in range(n_pre)]).to(dev)
+    x16 = ops.alloc2d(B, args.genes, device=dev)
+    e.reserve(B)
+
+    def resident_step(i):
+        ops.gather_rows(rowptr, colidx, values, args.genes, row_idx=idx_all[i], out16=x16)
+        e.draw_latents(B)
+        return e.train_step(x16)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        losses = resident_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms_resident = max_over_ranks(ev0.elapsed_time(ev1))
+    last_losses = [float(v) for v in losses]
+
+    # ---- end to end through the public API (host sampling, H2D indices+priors, D2H losses)
+    for _ in range(min(2, args.warmup)):
+        [float(v) for v in net.trainings_step(trainer.sample_cell_data())]
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        g, el, d = net.trainings_step(trainer.sample_cell_data())
+        _ = (float(g), float(el), float(d))           # the reference hands back host floats
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- encode-all-cells pass (E.predict over the whole matrix; each rank a row shard)
+    shard = (args.cells + world - 1) // world
+    r0, r1 = rank * shard, min(args.cells, (rank + 1) * shard)
+    enc_out = torch.empty((r1 - r0, Z), dtype=torch.float32, device=dev)
+    tile_rows = args.encode_tile
+    tile = ops.alloc2d(tile_rows, args.genes, device=dev)
+
+    def encode_shard():
+        for s in range(r0, r1, tile_rows):
+            m = min(tile_rows, r1 - s)
+            ops.gather_rows(rowptr, colidx, values, args.genes, row_start=s, n_rows=m,
+                            out16=tile[:m])
+            e.encode(tile[:m], out32=enc_out[s - r0:s - r0 + m])
+
+    encode_shard()
+    barrier()
+    ev0.record()
+    for _ in range(args.encode_reps):
+        encode_shard()
+    ev1.record()
+    barrier()
+    ms_enc = max_over_ranks(ev0.elapsed_time(ev1)) / args.encode_reps
+    ev0.record()
+    for _ in range(args.encode_reps):
+        host_enc = net.encoding_prediction(data) if world == 1 else None
+        if world > 1:
+            encode_shard()
+            host_enc = enc_out.cpu()
+    ev1.record()
+    barrier()
+    ms_enc_e2e = max_over_ranks(ev0.elapsed_time(ev1)) / args.encode_reps
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): events around every launch
+    gemm_ms, other = [], {}
+    if rank == 0:
+        real_gemm = ops.gemm
+        pairs = []
+
+        def timed_gemm(*a, **k):
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            real_gemm(*a, **k)
+            t.record()
+            pairs.append((s, t))
+
+        ops.gemm = timed_gemm
+        try:
+            reps = 2
+            ev0.record()
+            for i in range(reps):
+                resident_step(i)
+            ev1.record()
+            torch.cuda.synchronize()
+            inst_ms = ev0.elapsed_time(ev1) / reps
+            gemm_total = sum(s.elapsed_time(t) for s, t in pairs) / reps
+            gemm_ms = [gemm_total, len(pairs) // reps, inst_ms]
+        finally:
+            ops.gemm = real_gemm
+    if world > 1:
+        barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    step_ms = ms_resident / args.steps
+    value = B * world * args.steps / (ms_resident / 1e3)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+    gemm_total, gemm_launches, inst_ms = gemm_ms
+    flops_step = FLOP_PER_CELL_TRAIN * B
+    achieved_tf = flops_step / (gemm_total / 1e3) / 1e12
+    peak_tf = pk["bf16_tflops_sustained"]
+    line = {
+        "metric": "BiGAN train cells/sec", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(args, B),
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": "cells/s",
+                "h2d_bytes_per_step": B * 8 + 2 * B * Z * 4, "d2h_bytes_per_step": 12,
+                "ms_per_step": ms_e2e / args.steps,
+                "path": "CellTraining.sample_cell_data() + network.trainings_step(batch): host "
+                        "numpy sampling, pageable->device copy of the batch indices and priors, "
+                        "three loss floats read back per step"},
+        "gpu_launches": int(launches),
+        "roofline": {
+            "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Dense fwd/dgrad/wgrad)",
+            "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf, "traffic": None,
+            "peak_source": pk["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
+            "frac_of_burst_peak": achieved_tf / pk["bf16_tflops"],
+            "flops_per_step_algorithmic": flops_step,
+            "gemm_ms_per_step": gemm_total, "gemm_launches_per_step": gemm_launches,
+            "gemm_share_of_step": gemm_total / inst_ms,
+            "whole_step_tflops": flops_step / (step_ms / 1e3) / 1e12,
+            "whole_step_frac": flops_step / (step_ms / 1e3) / 1e12 / peak_tf,
+        },
+        "encode": {
+            "metric": "encode cells/sec (E.predict over all cells)",
+            "value": args.cells / (ms_enc / 1e3), "unit": "cells/s",
+            "e2e": args.cells / (ms_enc_e2e / 1e3), "cells": args.cells,
+            "tensor_frac": args.cells * FLOP_PER_CELL_ENCODE / (ms_enc / 1e3) / 1e12 /
+            (peak_tf * world), "d2h_bytes": args.cells * Z * 4,
+        },
+        "losses_last_step": last_losses, "setup_seconds": setup_s,
+        "precision_policy": "bf16 GEMM operands, fp32 accumulate; fp32 master weights + RMSprop "
+                            "slots; CELLCOMM_B200_SPLIT=" + os.environ.get("CELLCOMM_B200_SPLIT", "auto"),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in oracle_step_rate(
+            args.ref_batch, 1, 0, args.genes, "first step, no warm-up").items()
+            if k != "sec_per_step"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("CELLCOMM_BENCH_BATCH", "2048")),
+                    help="cells per GPU per trainings_step (reference default 128; 2048 saturates "
+                         "the tensor cores)")
+    ap.add_argument("--ref-batch", type=int, default=128,
+                    help="batch of the CPU arm's bounded sample (the reference's default)")
+    ap.add_argument("--cells", type=int, default=CELLS)
+    ap.add_argument("--genes", type=int, default=GENES)
+    ap.add_argument("--encode-tile", type=int, default=4096)
+    ap.add_argument("--encode-reps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

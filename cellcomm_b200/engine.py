@@ -192,9 +192,38 @@ def _pad(n, m=64):
 
 class _NoDist:
     world_size = 1
+    rank = 0
 
     def all_reduce(self, t):
         return t
+
+
+class TorchDist:
+    """Data-parallel plumbing over torch.distributed (NCCL over NVLink on the GPU box, gloo in
+    the CPU tests): sum all-reduces of BN statistics, flat gradients and the loss buffer.
+    Every rank holds the full weights and 1/world_size of each batch's rows."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_reduce(self, t):
+        if self.world_size > 1:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def default_dist():
+    """TorchDist when a process group is initialised (torchrun), else single-process."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return TorchDist()
+    except Exception:
+        pass
+    return _NoDist()
 
 
 class Net:
@@ -641,15 +670,16 @@ class Net:
                 x = A[i]
                 if c["bn_train"]:
                     ops.bn_bwd_stats(dy, x, L["save_mean"], L["save_rstd"], L["sums2"])
+                    if train:
+                        # dgamma / dbeta from the LOCAL sums: the flat gradient all-reduce in
+                        # apply_rmsprop() adds the other ranks' shares
+                        ops.bn_bwd_apply(dy, x, None, L["gamma"], L["save_mean"], L["save_rstd"],
+                                         L["sums2"], c["n_total"], L["dgamma"], L["dbeta"])
                     self.dist.all_reduce(L["sums2"])
                     if needs[i]:
                         self._emit(i, rows, state, lambda d: ops.bn_bwd_apply(
                             dy, x, d, L["gamma"], L["save_mean"], L["save_rstd"], L["sums2"],
-                            c["n_total"], L["dgamma"] if train else None,
-                            L["dbeta"] if train else None))
-                    elif train:
-                        ops.bn_bwd_apply(dy, x, None, L["gamma"], L["save_mean"], L["save_rstd"],
-                                         L["sums2"], c["n_total"], L["dgamma"], L["dbeta"])
+                            c["n_total"]))
                 else:
                     if train:
                         raise RuntimeError("training a BatchNormalization in inference mode")

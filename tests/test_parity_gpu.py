@@ -11,7 +11,8 @@ operands with fp32 accumulation vs the oracle's fp32):
                       tensor that carries >= 2 % of the network's gradient norm: cosine >= 0.95
                       (default precision level CELLCOMM_B200_SPLIT=1; level 3 reaches 0.99 /
                       0.985, see tests/test_precision_budget.py and DESIGN.md)
-    updated weights   max |dw_got - dw_ref| <= 5 % of the largest RMSprop step of that tensor
+    RMSprop updates   (w_after - w_before) from identical weights and slots: flat cosine
+                      >= 0.99, tensors with >= 2 % of the update norm >= 0.98
 
 Why gradients are compared per sub-step from synchronised weights: RMSprop's first step moves
 every weight by ~lr/sqrt(1-rho) = 0.019 whatever the gradient's size, which is larger than the
@@ -120,15 +121,16 @@ def test_every_substep_from_identical_weights(variant, Z, G, B):
                 continue       # near-zero tensors (biases in front of a BN): flat cosine only
             c = _cos(a, b)
             assert c >= 0.95, f"sub-step {k} {net} grad tensor {i}: cosine {c}"
-        # the RMSprop update itself, from identical weights and slots
+        # the RMSprop update itself (w_after - w_before), from identical weights and slots
         after_ref = orc.get_weights(net)
         after_got = e.nets[net].get_weights()
-        for i, (w0, w1, wg) in enumerate(zip(before[net], after_ref, after_got)):
-            if w0.numel() == 0:
-                continue
-            step = (w1 - w0).abs().max().item()
-            err = np.abs(wg - w1.numpy()).max()
-            assert err <= 0.05 * step + 1e-6, f"sub-step {k} {net} tensor {i}: {err} vs step {step}"
+        du_r = [(w1 - w0).numpy().ravel() for w0, w1 in zip(before[net], after_ref)]
+        du_g = [(wg - w0.numpy()).ravel() for w0, wg in zip(before[net], after_got)]
+        fr, fg = np.concatenate(du_r), np.concatenate(du_g)
+        assert _cos(fg, fr) >= 0.99, f"sub-step {k} {net}: update cosine {_cos(fg, fr)}"
+        for i, (a, b) in enumerate(zip(du_g, du_r)):
+            if b.size and np.linalg.norm(b) >= 2e-2 * np.linalg.norm(fr):
+                assert _cos(a, b) >= 0.98, f"sub-step {k} {net} tensor {i}: update cosine {_cos(a, b)}"
 
 
 @pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 2000, 128), ("classify", 10, 600, 64)])

@@ -190,15 +190,15 @@ def test_losses():
     cols = 3370
     pred, tgt = _r(rows, cols, 9), _r(rows, cols, 10)
     loss = torch.zeros(1, device="cuda")
-    dp = ops.alloc2d(rows, cols)
-    ops.mse_fwd_bwd(_dev(pred, ops), rows, loss, target16=_dev(tgt, ops), dpred16=dp)
+    dp = ops.alloc2d(rows, cols, dtype=torch.float32)
+    ops.mse_fwd_bwd(_dev(pred, ops), rows, loss, target=_dev(tgt, ops), dpred=dp)
     d = pred.float() - tgt.float()
     assert abs(loss.item() - (d * d).mean().item()) < 1e-4 * (d * d).mean().item()
     close16(dp, 2 * d / (rows * cols), atol=1e-9)
     t32 = torch.rand(rows, 3, device="cuda")
     p3 = _r(rows, 3, 11)
     loss = torch.zeros(1, device="cuda")
-    ops.mse_fwd_bwd(_dev(p3, ops), rows, loss, target32=t32)
+    ops.mse_fwd_bwd(_dev(p3, ops), rows, loss, target=t32)
     assert abs(loss.item() - ((p3.float() - t32.cpu()) ** 2).mean().item()) < 1e-5
 
 
@@ -234,3 +234,69 @@ def test_rmsprop_matches_keras_formula():
     ref = b32.cpu() - lr * bg.cpu() / torch.sqrt(0.15 * bg.cpu() ** 2 + eps)
     ops.rmsprop_step(b32, None, bg, bms, bmom, lr, rho, mo, eps)
     assert torch.allclose(b32.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_fp32_operands_bias_grad_and_split():
+    """dtype-mask paths: fp32 activations / gradients, fp32 bias gradient, bf16 hi+lo split."""
+    ops = _ops()
+    rows, cols = 96, 333
+    x32 = torch.randn(rows, cols, device="cuda") * 0.05 + 0.5
+    # split: hi + lo reproduces x to ~16 bits
+    hi, lo = ops.alloc2d(rows, cols), ops.alloc2d(rows, cols)
+    ops.split_bf16(x32, hi, lo)
+    assert torch.equal(hi, x32.to(torch.bfloat16))
+    assert (hi.float() + lo.float() - x32).abs().max().item() <= 2 ** -16
+    # fp32 -> fp32 dropout with explicit mask, fp32 -> bf16 BN
+    mask = (torch.rand(rows, cols, device="cuda") > 0.1).to(torch.uint8)
+    d32 = torch.empty(rows, cols, device="cuda")
+    ops.dropout(x32, d32, 0.1, mask=mask)
+    assert torch.allclose(d32, x32 * mask.float() / 0.9, rtol=1e-6, atol=1e-7)
+    sums = torch.empty(2 * cols, device="cuda")
+    ops.bn_stats(d32, sums)
+    gamma, beta = torch.ones(cols, device="cuda"), torch.zeros(cols, device="cuda")
+    mm, mv = torch.zeros(cols, device="cuda"), torch.ones(cols, device="cuda")
+    sm, sr = torch.empty(cols, device="cuda"), torch.empty(cols, device="cuda")
+    y = ops.alloc2d(rows, cols)
+    ops.bn_train_apply(d32, y, sums, rows, gamma, beta, 1e-3, 0.99, mm, mv, sm, sr)
+    ref = (d32 - d32.mean(0)) / torch.sqrt(d32.var(0, unbiased=False) + 1e-3)
+    close16(y, ref.cpu(), atol=2e-2)
+    # fp32 dy through BN backward into fp32 dx
+    dy32 = torch.randn(rows, cols, device="cuda")
+    s2 = torch.empty(2 * cols, device="cuda")
+    ops.bn_bwd_stats(dy32, d32, sm, sr, s2)
+    dx32 = torch.empty(rows, cols, device="cuda")
+    ops.bn_bwd_apply(dy32, d32, dx32, gamma, sm, sr, s2, rows)
+    xt = d32.clone().requires_grad_(True)
+    yy = (xt - xt.mean(0)) / torch.sqrt(xt.var(0, unbiased=False) + 1e-3)
+    yy.backward(dy32)
+    assert torch.allclose(dx32, xt.grad, rtol=2e-3, atol=2e-3)
+    # act_bwd fp32 dy, fp32 y -> bf16 dz ; bias_grad from the fp32 operands
+    ysig = torch.sigmoid(torch.randn(rows, cols, device="cuda"))
+    dz = ops.alloc2d(rows, cols)
+    ops.act_bwd(dy32, ysig, dz, ops.ACT_SIGMOID)
+    close16(dz, (dy32 * ysig * (1 - ysig)).cpu())
+    db = torch.empty(cols, device="cuda")
+    ops.bias_grad(dy32, ysig, ops.ACT_SIGMOID, db)
+    assert torch.allclose(db, (dy32 * ysig * (1 - ysig)).sum(0), rtol=1e-4, atol=1e-4)
+    ops.bias_grad(dy32, ysig, ops.ACT_NONE, db)
+    assert torch.allclose(db, dy32.sum(0), rtol=1e-4, atol=1e-4)
+    # copy2d as cast + scale + accumulate across dtypes
+    acc = torch.ones(rows, cols, device="cuda")
+    ops.copy2d(hi, acc, beta=1, scale=2.0)
+    assert torch.allclose(acc, 1 + 2 * hi.float())
+    # dgrad into an fp32 gradient buffer with accumulate
+    K, N = 200, 150
+    dzz = ops.alloc2d(rows, N)
+    dzz.normal_()
+    w = ops.alloc2d(K, N)
+    w.normal_()
+    g32 = torch.ones(rows, K, device="cuda")
+    ops.dense_dgrad([dzz], [w], g32, beta=1)
+    assert torch.allclose(g32, 1 + dzz.float() @ w.float().t(), rtol=1e-3, atol=1e-2)
+    # wgrad with hi/lo x segments and two dz terms
+    xw = torch.randn(rows, K, device="cuda")
+    xh, xl = ops.alloc2d(rows, K), ops.alloc2d(rows, K)
+    ops.split_bf16(xw, xh, xl)
+    dw = torch.empty(K, N, device="cuda")
+    ops.dense_wgrad([xh, xl], dzz, dw)
+    assert torch.allclose(dw, xw.t() @ dzz.float(), rtol=1e-3, atol=2e-3)
