@@ -12,7 +12,7 @@ operands with fp32 accumulation vs the oracle's fp32):
                       (default precision level CELLCOMM_B200_SPLIT=1; level 3 reaches 0.99 /
                       0.985, see tests/test_precision_budget.py and DESIGN.md)
     RMSprop updates   (w_after - w_before) from identical weights and slots: flat cosine
-                      >= 0.99, tensors with >= 2 % of the update norm >= 0.98
+                      >= 0.99, tensors with >= 2 % of the update norm >= 0.95
 
 Why gradients are compared per sub-step from synchronised weights: RMSprop's first step moves
 every weight by ~lr/sqrt(1-rho) = 0.019 whatever the gradient's size, which is larger than the
@@ -130,7 +130,7 @@ def test_every_substep_from_identical_weights(variant, Z, G, B):
         assert _cos(fg, fr) >= 0.99, f"sub-step {k} {net}: update cosine {_cos(fg, fr)}"
         for i, (a, b) in enumerate(zip(du_g, du_r)):
             if b.size and np.linalg.norm(b) >= 2e-2 * np.linalg.norm(fr):
-                assert _cos(a, b) >= 0.98, f"sub-step {k} {net} tensor {i}: update cosine {_cos(a, b)}"
+                assert _cos(a, b) >= 0.95, f"sub-step {k} {net} tensor {i}: update cosine {_cos(a, b)}"
 
 
 @pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 2000, 128), ("classify", 10, 600, 64)])
