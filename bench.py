@@ -60,8 +60,9 @@ def synth_csr(n_cells, n_genes, seed, device):
     logp = logp[torch.randperm(n_genes, generator=g, device=device)]
     rowptr = np.zeros(n_cells + 1, dtype=np.int64)
     np.cumsum(nnz_row, out=rowptr[1:])
-    colidx = torch.empty(int(rowptr[-1]), dtype=torch.int32, device=device)
     kmax = int(nnz_row.max())
+    nnz_dev = torch.from_numpy(nnz_row).to(device)
+    parts = []
     chunk = 2048
     for s in range(0, n_cells, chunk):
         e = min(n_cells, s + chunk)
@@ -72,11 +73,14 @@ def synth_csr(n_cells, n_genes, seed, device):
         for rep in range((n_genes + n_cells - 1) // n_cells):
             forced = rows + rep * n_cells
             ok = forced < n_genes
-            keys[ok, forced[ok]] = float("inf")
+            keys[torch.nonzero(ok).flatten(), forced[ok]] = float("inf")
         top = torch.topk(keys, kmax, dim=1).indices
-        for i in range(e - s):
-            k = int(nnz_row[s + i])
-            colidx[rowptr[s + i]:rowptr[s + i] + k] = torch.sort(top[i, :k]).values.to(torch.int32)
+        keep = torch.arange(kmax, device=device)[None, :] < nnz_dev[s:e, None]
+        top = torch.where(keep, top, torch.full_like(top, n_genes))   # drop the surplus picks
+        top = torch.sort(top, dim=1).values                            # ascending, surplus last
+        parts.append(top[keep.sum(1, keepdim=True) > torch.arange(kmax, device=device)[None, :]])
+    colidx = torch.cat(parts).to(torch.int32)
+    assert colidx.numel() == int(rowptr[-1])
     nnz = int(rowptr[-1])
     geo = torch.floor(torch.log(torch.rand(nnz, generator=g, device=device).clamp_min(1e-20)) /
                       float(np.log(1 - 0.45)))

@@ -29,7 +29,8 @@ class GemmDesc(C.Structure):
         ("out32", vp), ("ld32", c_i64), ("beta32", c_i32),
         ("workspace", vp), ("workspace_elems", c_i64),
         ("force_splits", c_i32), ("force_bn", c_i32),
-        ("reserved", c_i32 * 6),
+        ("rms_p32", vp), ("rms_ms", vp), ("rms_mom", vp), ("rms_p16", vp), ("rms_ld", c_i64),
+        ("rms_lr", c_f32), ("rms_rho", c_f32), ("rms_momentum", c_f32), ("rms_eps", c_f32),
     ]
 
 

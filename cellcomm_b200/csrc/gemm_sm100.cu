@@ -44,6 +44,13 @@ struct EpiParams {
   float* out32;
   long long ld32;
   int beta32;
+  // fused Keras RMSprop(momentum) on the tile (wgrad epilogue): the accumulator IS the gradient
+  float* rms_p32;
+  float* rms_ms;
+  float* rms_mom;
+  bf16* rms_p16;
+  long long rms_ld;
+  float rms_lr, rms_rho, rms_momentum, rms_eps;
 };
 
 struct GemmParams {
@@ -205,6 +212,78 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& e, int r, int 
   }
 }
 
+// Epilogue math only (bias, activation, act' multiply) on a thread's 32 columns of row r.
+__device__ __forceinline__ void epilogue_math32(const EpiParams& e, int r, int c0, float (&v)[32]) {
+  const int ncols = min(32, e.N - c0);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = v[j] * e.alpha;
+    if (e.bias != nullptr && j < ncols) x += __ldg(e.bias + c0 + j);
+    if (e.act == CC_ACT_SIGMOID) x = sigmoidf_(x);
+    else if (e.act == CC_ACT_RELU) x = fmaxf(x, 0.f);
+    v[j] = x;
+  }
+  if (e.dact != 0 && r < e.M) {
+    const bf16* yrow = e.dact_y + (long long)r * e.ld_dact + c0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols) {
+        float y = bf2f(yrow[j]);
+        v[j] *= (e.dact == CC_ACT_SIGMOID) ? y * (1.f - y) : (y > 0.f ? 1.f : 0.f);
+      }
+    }
+  }
+}
+
+// Coalesced store of a warp's 32 x 32 block (thread `lane` holds row r0+lane, columns
+// c0..c0+31): transpose through a padded smem tile so that every store instruction writes one
+// contiguous row segment (128 B fp32 / 64 B bf16) instead of 32 scattered 16-byte pieces.
+__device__ __forceinline__ void epilogue_store_coalesced(const EpiParams& e, float* stage /*32x33*/,
+                                                         int lane, int r0, int c0,
+                                                         const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+  __syncwarp();
+  const int c = c0 + lane;
+  const bool col_ok = c < e.N;
+  const int rows = min(32, e.M - r0);
+  if (e.rms_p32 != nullptr && col_ok) {
+    // ms = rho*ms + (1-rho) g^2 ; mom = momentum*mom + lr*g/sqrt(ms+eps) ; w -= mom
+    long long off = (long long)r0 * e.rms_ld + c;
+    for (int rr = 0; rr < rows; ++rr, off += e.rms_ld) {
+      const float g = stage[rr * 33 + lane];
+      const float ms = e.rms_rho * e.rms_ms[off] + (1.f - e.rms_rho) * g * g;
+      const float mo = e.rms_momentum * e.rms_mom[off] + e.rms_lr * g * rsqrtf(ms + e.rms_eps);
+      const float w = e.rms_p32[off] - mo;
+      e.rms_ms[off] = ms;
+      e.rms_mom[off] = mo;
+      e.rms_p32[off] = w;
+      if (e.rms_p16 != nullptr) e.rms_p16[off] = f2bf(w);
+    }
+  }
+  if (e.out32 != nullptr) {
+    float* o = e.out32 + (long long)r0 * e.ld32 + c;
+    if (e.beta32) {
+      for (int rr = 0; rr < rows; ++rr, o += e.ld32)
+        if (col_ok) *o += stage[rr * 33 + lane];
+    } else {
+      for (int rr = 0; rr < rows; ++rr, o += e.ld32)
+        if (col_ok) *o = stage[rr * 33 + lane];
+    }
+  }
+  if (e.out16 != nullptr) {
+    bf16* o = e.out16 + (long long)r0 * e.ld16 + c;
+    if (e.beta16) {
+      for (int rr = 0; rr < rows; ++rr, o += e.ld16)
+        if (col_ok) *o = f2bf(bf2f(*o) + stage[rr * 33 + lane]);
+    } else {
+      for (int rr = 0; rr < rows; ++rr, o += e.ld16)
+        if (col_ok) *o = f2bf(stage[rr * 33 + lane]);
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------- kernel
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(128, 2)
@@ -345,6 +424,174 @@ gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
       } else {
         epilogue_store32(p.epi, r, n0 + c, v);
       }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                 "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------- persistent warp-specialised kernel
+// One CTA per SM loops over output tiles (m fastest, so concurrently running CTAs share the
+// same B / weight tile through L2).  192 threads: warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2-5 = epilogue.  The fp32 accumulator is double-buffered in TMEM (2 x BN columns), so
+// the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring has STAGES
+// k-blocks in flight across tile boundaries.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p,
+                               const int tiles_m, const int tiles_n) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+  static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 4));
+  // per-epilogue-warp 32x33 fp32 transpose tiles, after the barrier block
+  float* epi_stage = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 6));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nkb = p.total_kblocks;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BM;
+      const int n0 = (tile / tiles_m) * BN;
+      int seg = 0, kb_in_seg = 0;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 11);
+        if (lane == 0) {
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          const int k0 = kb_in_seg * BK;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0);
+          } else {
+            tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
+          } else {
+            tma_load_2d(b_dst, &maps.b[seg], full_bar(s), k0, n0);
+          }
+        }
+        __syncwarp();
+        if (++kb_in_seg >= p.kblocks[seg] && seg < p.nseg - 1) {
+          kb_in_seg = 0;
+          ++seg;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), aph ^ 1u, 12);  // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_acc + acc * BN;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph, 13);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_src = smem_base + s * STAGE_BYTES;
+          const uint32_t b_src = a_src + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = p.adesc_hi | (uint64_t)(((a_src + k * p.a_kstep) & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = p.bdesc_hi | (uint64_t)(((b_src + k * p.b_kstep) & 0x3FFFFu) >> 4);
+            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+          if (i == nkb - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..5 =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile % tiles_m) * BM;
+      const int n0 = (tile / tiles_m) * BN;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), aph, 14);
+      tcgen05_fence_after();
+      const int r = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.epi.N) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld32(t_row + (uint32_t)c, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        epilogue_math32(p.epi, r, n0 + c, v);
+        epilogue_store_coalesced(p.epi, epi_stage + q * (32 * 33), lane, m0 + q * 32, n0 + c, v);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
   tcgen05_fence_before();
@@ -505,13 +752,47 @@ static int launch_major(const TmaMaps& maps, const GemmParams& p, dim3 grid, boo
   return launch_cfg<BN, STAGES, true, false>(maps, p, grid, st);
 }
 
+template <int BN, int STAGES>
+static constexpr size_t smem_bytes_persistent() {
+  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 6) + 4 * 32 * 33 * 4 + 1024;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_persistent_cfg(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
+                                 int num_sms, cudaStream_t st) {
+  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;
+  constexpr size_t smem = smem_bytes_persistent<BN, STAGES>();
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int tiles = mt * nt;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, 192, smem, st>>>(maps, p, mt, nt);
+  CC_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_persistent(const TmaMaps& maps, const GemmParams& p, int mt, int nt, int num_sms,
+                             bool a_mn, bool b_mn, cudaStream_t st) {
+  if (!a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, false, true>(maps, p, mt, nt, num_sms, st);
+  if (!a_mn && !b_mn) return launch_persistent_cfg<BN, STAGES, false, false>(maps, p, mt, nt, num_sms, st);
+  if (a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, true, true>(maps, p, mt, nt, num_sms, st);
+  return launch_persistent_cfg<BN, STAGES, true, false>(maps, p, mt, nt, num_sms, st);
+}
+
 static int g_num_sms = 0;
 
 int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   CC_REQUIRE(d != nullptr, "cc_gemm: null descriptor");
   CC_REQUIRE(d->M > 0 && d->N > 0, "cc_gemm: empty output %dx%d", d->M, d->N);
   CC_REQUIRE(d->nseg >= 1 && d->nseg <= MAX_SEG, "cc_gemm: nseg=%d out of range", d->nseg);
-  CC_REQUIRE(d->out16 != nullptr || d->out32 != nullptr, "cc_gemm: no output");
+  CC_REQUIRE(d->out16 != nullptr || d->out32 != nullptr || d->rms_p32 != nullptr,
+             "cc_gemm: no output");
+  CC_REQUIRE(d->rms_p32 == nullptr || (d->rms_ms != nullptr && d->rms_mom != nullptr),
+             "cc_gemm: fused RMSprop needs ms and mom");
   if (g_num_sms == 0) {
     int dev = 0;
     CC_CHECK_CUDA(cudaGetDevice(&dev));
@@ -579,12 +860,21 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.out32 = d->out32;
   e.ld32 = d->ld32;
   e.beta32 = d->beta32;
+  e.rms_p32 = d->rms_p32;
+  e.rms_ms = d->rms_ms;
+  e.rms_mom = d->rms_mom;
+  e.rms_p16 = (bf16*)d->rms_p16;
+  e.rms_ld = d->rms_ld;
+  e.rms_lr = d->rms_lr;
+  e.rms_rho = d->rms_rho;
+  e.rms_momentum = d->rms_momentum;
+  e.rms_eps = d->rms_eps;
 
   const int mt = (d->M + BM - 1) / BM, nt = (d->N + bn - 1) / bn;
   // split-K when the tile grid cannot fill the machine and the reduction is long
   int splits = 1;
   const long long Mpad = (long long)mt * BM, Npad = (long long)nt * bn;
-  if (d->workspace != nullptr) {
+  if (d->workspace != nullptr && d->rms_p32 == nullptr) {
     int want = d->force_splits ? d->force_splits : env_int("CC_GEMM_SPLITS", 0);
     if (want == 0) {
       const int tiles = mt * nt;
@@ -612,6 +902,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     p.kb_per_split = total;
     splits = 1;
   }
+
+  if (splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr)) {
+    if (bn == 256) return launch_persistent<256, 4>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
+    return launch_persistent<128, 6>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
+  }
+  CC_REQUIRE(d->rms_p32 == nullptr, "cc_gemm: fused RMSprop is not available with split-K");
 
   dim3 grid((unsigned)nt, (unsigned)mt, (unsigned)splits);
   int rc;

@@ -243,6 +243,8 @@ class Net:
         self.grad = {}     # activation gradients, always fp32
         self.tmp = {}      # fp32 scratch for accumulating a second gradient contribution
         self.dzb = {}      # bf16 gradient w.r.t. a Dense pre-activation (GEMM operand)
+        self.fuse_optimizer = False   # kernels updated inside the wgrad epilogue (1 GPU)
+        self.keep_grads = False       # fused mode: also write dW (parity tests)
         self.hp, self.split = self._high_precision_tensors()
         self.split_lo = {}  # bf16 low-order terms of the split tensors
         self._needs_cache = {}
@@ -254,17 +256,26 @@ class Net:
         dev = self.device
         off = 0
         meta = []
+        # flat layout: every Dense kernel first, then all biases and BN gamma/beta ("small"
+        # parameters) contiguously, so that with the kernels updated inside the wgrad epilogue
+        # one extra launch over the tail updates everything else
         for lay in self.g.layers:
             if lay[0] == "dense":
                 K, N = sum(lay[1]), lay[2]
                 ldn = ops.pad_ld(N)
                 meta.append({"kind": "dense", "K": K, "N": N, "ld": ldn, "w_off": off,
-                             "b_off": off + K * ldn, "act": lay[3], "in_widths": lay[1]})
-                off += K * ldn + _pad(N)
+                             "act": lay[3], "in_widths": lay[1]})
+                off += K * ldn
             else:
-                n = lay[1]
-                meta.append({"kind": "bn", "n": n, "g_off": off, "be_off": off + _pad(n)})
-                off += 2 * _pad(n)
+                meta.append({"kind": "bn", "n": lay[1]})
+        self.small_off = off
+        for m in meta:
+            if m["kind"] == "dense":
+                m["b_off"] = off
+                off += _pad(m["N"])
+            else:
+                m["g_off"], m["be_off"] = off, off + _pad(m["n"])
+                off += 2 * _pad(m["n"])
         self.n_flat = max(off, 64)
         self.p32 = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
         self.g32 = torch.zeros_like(self.p32)
@@ -279,7 +290,7 @@ class Net:
                 wv = lambda buf: buf[m["w_off"]:m["w_off"] + K * ld].view(K, ld)[:, :N]
                 bv = lambda buf: buf[m["b_off"]:m["b_off"] + N]
                 L.update(w32=wv(self.p32), w16=wv(self.p16), dw=wv(self.g32), b32=bv(self.p32),
-                         db=bv(self.g32))
+                         db=bv(self.g32), ms_w=wv(self.ms), mom_w=wv(self.mom))
                 fan = K + N
                 if K > 0 and N > 0:
                     limit = math.sqrt(6.0 / fan)      # glorot_uniform (Keras Dense default)
@@ -639,19 +650,27 @@ class Net:
                 for i in node["ins"]:
                     k = g.widths[i]
                     if k > 0:
-                        if train:
-                            xs = c["operands"][i]
-                            # all hi/lo cross terms except lo*lo
-                            pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
-                                     if a + b < 2]
-                            ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs],
-                                            L["dw"][ro:ro + k])
+                        # input gradient first: it must see this layer's weights BEFORE the
+                        # fused wgrad epilogue below updates them
                         if needs[i]:
                             wseg = L["w16"][ro:ro + k]
                             dst = self._buf(self.grad, i)[:rows]
                             ops.dense_dgrad(dzs, [wseg] * len(dzs), dst,
                                             beta=1 if state[i] else 0)
                             state[i] = True
+                        if train:
+                            xs = c["operands"][i]
+                            # all hi/lo cross terms except lo*lo
+                            pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
+                                     if a + b < 2]
+                            rms = None
+                            if self.fuse_optimizer:
+                                sl = slice(ro, ro + k)
+                                rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
+                                       LR, RHO, MOMENTUM, EPSILON)
+                            dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
+                            ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs], dw,
+                                            rms=rms)
                     ro += k
                 if train:
                     if out in self.prebn:
@@ -715,9 +734,17 @@ class Net:
 
     # ------------------------------------------------------------------ optimiser
     def apply_rmsprop(self):
-        """Keras RMSprop(lr=0.0075, rho=0.85, momentum=0.1) over the whole flat parameter
-        buffer in one launch; padding has zero gradient and stays zero.  In data-parallel runs
-        the flat gradient is all-reduced (sum of per-rank partial sums) first."""
+        """Keras RMSprop(lr=0.0075, rho=0.85, momentum=0.1) over the flat parameter buffer in
+        one launch; padding has zero gradient and stays zero.  In data-parallel runs the flat
+        gradient is all-reduced (sum of per-rank partial sums) first.  With `fuse_optimizer`
+        the Dense kernels were already updated inside their wgrad epilogues (the gradient
+        never went to HBM) and only the small tail (biases, BN gamma/beta) is updated here."""
+        if self.fuse_optimizer:
+            sl = slice(self.small_off, self.n_flat)
+            if self.n_flat > self.small_off:
+                ops.rmsprop_step(self.p32[sl], self.p16[sl], self.g32[sl], self.ms[sl],
+                                 self.mom[sl], LR, RHO, MOMENTUM, EPSILON)
+            return
         self.dist.all_reduce(self.g32)
         ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
                          EPSILON)
@@ -807,11 +834,21 @@ class BiGanEngine:
         self.E = Net(graphs["E"], max_batch, self.device, gen, self.dist)
         self.D = Net(graphs["D"], max_batch, self.device, gen, self.dist)
         self.nets = {"G": self.G, "E": self.E, "D": self.D}
+        self.set_fused_optimizer(self.dist.world_size == 1 and
+                                 os.environ.get("CELLCOMM_B200_FUSE_OPT", "1") != "0")
         self.loss_buf = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.max_batch = 0
         self.reserve(max_batch)
+
+    def set_fused_optimizer(self, on, keep_grads=False):
+        """Single-GPU: apply RMSprop to every Dense kernel inside its wgrad GEMM epilogue.
+        keep_grads also writes the gradients (parity tests compare them)."""
+        if on and self.dist.world_size > 1:
+            raise ValueError("the fused optimiser needs the gradient all-reduce to be a no-op")
+        for n in self.nets.values():
+            n.fuse_optimizer, n.keep_grads = bool(on), bool(keep_grads)
 
     def reserve(self, rows):
         """(Re)allocate the per-step staging buffers for batches of up to `rows` rows."""

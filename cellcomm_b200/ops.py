@@ -77,7 +77,8 @@ def launch_count():
 
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
-         alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True):
+         alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
+         rms=None):
     lib = _lib.load()
     d = GemmDesc()
     d.M, d.N = int(M), int(N)
@@ -103,6 +104,19 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
         ws = workspace(a_list[0].device)
         d.workspace, d.workspace_elems = ws.data_ptr(), ws.numel()
     d.force_splits, d.force_bn = int(splits), int(bn)
+    if rms is not None:
+        p32, p16, ms, mom, lr, rho, momentum, eps = rms
+        for t, name in ((p32, "p32"), (ms, "ms"), (mom, "mom")):
+            _req(t, torch.float32, name)
+            if tuple(t.shape) != (M, N) or _ld(t) != _ld(p32):
+                raise ValueError("gemm(rms=...): parameter / slot views must be [M, N] with one ld")
+        d.rms_p32, d.rms_ms, d.rms_mom, d.rms_p16 = p32.data_ptr(), ms.data_ptr(), \
+            mom.data_ptr(), _p(p16)
+        if p16 is not None and _ld(p16) != _ld(p32):
+            raise ValueError("gemm(rms=...): p16 must share the parameter's leading dimension")
+        d.rms_ld = _ld(p32)
+        d.rms_lr, d.rms_rho, d.rms_momentum, d.rms_eps = float(lr), float(rho), float(momentum), \
+            float(eps)
     check(lib.cc_gemm(C.byref(d), _stream()))
 
 
@@ -130,13 +144,17 @@ def dense_dgrad(dzs, ws16, out, *, dact_y=None, dact=0, alpha=1.0, beta=0):
          **kw)
 
 
-def dense_wgrad(x, dz, dw32, beta=0):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None):
     """dw32[K,N] (+)= x[M,K]^T @ dz[M,N].  x may be a list [hi, lo] (bf16 expansion): the
-    terms accumulate as GEMM segments along the batch reduction."""
-    K, N = dw32.shape
+    terms accumulate as GEMM segments along the batch reduction.
+    rms = (p32, p16, ms, mom, lr, rho, momentum, eps): fuse the Keras RMSprop update of that
+    [K,N] parameter block into the epilogue (dw32 may then be None: the gradient is consumed
+    in registers and never written)."""
+    K, N = (dw32.shape if dw32 is not None else rms[0].shape)
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
-    gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta, use_ws=False)
+    gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta, use_ws=False,
+         rms=rms)
 
 
 # --------------------------------------------------------------------------- data

@@ -100,6 +100,7 @@ int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_dev, const f
  *   if dact:   v *= act'(y[r,c])   (1: y(1-y)  2: y>0)   y = dact_y (bf16)
  *   if out32:  out32[r,c] = v + (beta32 ? out32[r,c] : 0)
  *   if out16:  out16[r,c] = bf16(v + (beta16 ? out16[r,c] : 0))
+ *   if rms_p32: fused RMSprop update of the parameter block with gradient v (see below)
  */
 enum { CC_ACT_NONE = 0, CC_ACT_SIGMOID = 1, CC_ACT_RELU = 2 };
 #define CC_GEMM_MAX_SEG 4
@@ -132,7 +133,18 @@ typedef struct cc_gemm_desc {
   /* tuning / debug overrides, 0 = automatic */
   int32_t force_splits;
   int32_t force_bn;
-  int32_t reserved[6];
+  /* optional fused optimiser (weight-gradient GEMMs): when rms_p32 != NULL the epilogue
+   * treats v as the gradient of the [M,N] parameter block at rms_p32 (leading dimension
+   * rms_ld, shared by rms_ms / rms_mom / rms_p16) and applies Keras RMSprop(momentum)
+   * in place -- ms = rho*ms + (1-rho) v^2; mom = momentum*mom + lr*v/sqrt(ms+eps);
+   * w -= mom; p16 = bf16(w) -- so the gradient never round-trips through HBM
+   * (optimizers.RMSprop, src/bigan_classify.py:88).  out32/out16 stay optional. */
+  float* rms_p32;
+  float* rms_ms;
+  float* rms_mom;
+  void* rms_p16;
+  int64_t rms_ld;
+  float rms_lr, rms_rho, rms_momentum, rms_eps;
 } cc_gemm_desc;
 
 int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);

@@ -68,13 +68,17 @@ def dense_dgrad(dzs, ws16, out16, *, dact_y=None, dact=0, alpha=1.0, beta=0):
     _store(out16, acc.float(), beta)
 
 
-def dense_wgrad(x, dz, dw32, beta=0):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None):
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
     acc = 0
     for t, d in zip(xs, dzs):
         acc = acc + t.double().t() @ d.double()
-    _store(dw32, acc.float(), beta)
+    g = acc.float()
+    if rms is not None:
+        p32, p16, ms, mom, lr, rho, momentum, eps = rms
+        rmsprop_step(p32, p16, g, ms, mom, lr, rho, momentum, eps)
+    _store(dw32, g, beta)
 
 
 def bias_grad(dy, y, act, out32):

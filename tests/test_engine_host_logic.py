@@ -19,9 +19,10 @@ def _emulated_ops(monkeypatch):
     yield
 
 
-def _pair(variant, Z, G, B, seed=0):
+def _pair(variant, Z, G, B, seed=0, fused=True):
     orc = O.OracleBiGan(variant, Z, G, seed=seed, dtype=torch.float64)
     e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cpu", seed=seed)
+    e.set_fused_optimizer(fused, keep_grads=True)
     for n in ("G", "E", "D"):
         e.nets[n].set_weights([w.numpy() for w in orc.get_weights(n)])
     return orc, e
@@ -47,10 +48,12 @@ def _close(a, b, rtol=2e-4, atol=2e-6, what=""):
     assert np.all(err <= tol), f"{what}: max err {err.max():.3e} (ref max {np.abs(b).max():.3e})"
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 200, 16), ("classify", 4, 60, 12),
                                            ("cont", 8, 5, 3)])
-def test_trainings_step_matches_oracle(variant, Z, G, B):
-    orc, e = _pair(variant, Z, G, B)
+def test_trainings_step_matches_oracle(variant, Z, G, B, fused):
+    """fused: RMSprop applied inside the wgrad epilogue (single GPU); else one flat sweep"""
+    orc, e = _pair(variant, Z, G, B, fused=fused)
     for step in range(2):
         x, z, r = _inputs(variant, Z, G, B, 100 + step)
         masks = O.make_masks(variant, Z, G, B, 7 + step)

@@ -197,3 +197,39 @@ def test_large_batch_shapes():
     ops.gemm(M, N, [da], [db], [K], 0, 1, out16=out16)
     torch.cuda.synchronize()
     _check(out16, a.float() @ b.float(), K, True)
+
+
+@pytest.mark.parametrize("K,N,B", [(200, 170, 128), (700, 40, 64), (129, 513, 300)])
+def test_wgrad_with_fused_rmsprop_epilogue(K, N, B):
+    """dW = X^T dZ consumed in the epilogue by Keras RMSprop(momentum): parameters, slots and
+    the bf16 copy are updated in place; the gradient is optionally also written."""
+    ops = _ops()
+    x, dz = _rand(B, K, 80, 0.5), _rand(B, N, 81, 0.01)
+    ld = ops.pad_ld(N)
+    dev = "cuda"
+    w0 = torch.randn(K, N) * 0.05
+    ms0 = torch.rand(K, N) * 1e-4
+    mom0 = torch.randn(K, N) * 1e-3
+    mk = lambda t, dt=torch.float32: (lambda b: (b.copy_(t), b)[1])(
+        torch.zeros(K, ld, dtype=dt, device=dev)[:, :N])
+    p32, ms, mom = mk(w0), mk(ms0), mk(mom0)
+    p16 = torch.zeros(K, ld, dtype=torch.bfloat16, device=dev)[:, :N]
+    dw = torch.zeros(K, ld, device=dev)[:, :N]
+    lr, rho, mo, eps = 0.0075, 0.85, 0.1, 1e-7
+    ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), dw, rms=(p32, p16, ms, mom, lr, rho, mo, eps))
+    torch.cuda.synchronize()
+    g = x.float().t() @ dz.float()
+    _check(dw, g, B, False, scale=0.005)
+    g = dw.cpu()                      # the kernel's own fp32 gradient
+    ms_ref = rho * ms0 + (1 - rho) * g * g
+    mom_ref = mo * mom0 + lr * g / torch.sqrt(ms_ref + eps)
+    assert torch.allclose(ms.cpu(), ms_ref, rtol=1e-5, atol=1e-12)
+    assert torch.allclose(mom.cpu(), mom_ref, rtol=1e-4, atol=1e-8)
+    assert torch.allclose(p32.cpu(), w0 - mom_ref, rtol=1e-5, atol=1e-7)
+    assert torch.equal(p16, p32.to(torch.bfloat16))
+    # without a gradient output
+    p32b, msb, momb = mk(w0), mk(ms0), mk(mom0)
+    ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), None,
+                    rms=(p32b, None, msb, momb, lr, rho, mo, eps))
+    torch.cuda.synchronize()
+    assert torch.equal(p32b, p32) and torch.equal(msb, ms)

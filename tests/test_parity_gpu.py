@@ -41,10 +41,11 @@ def _cos(a, b):
     return float(a @ b / (na * nb))
 
 
-def _setup(variant, Z, G, B, seed=0):
+def _setup(variant, Z, G, B, seed=0, fused=True):
     from cellcomm_b200 import engine as eng
     orc = O.OracleBiGan(variant, Z, G, seed=seed, dtype=torch.float32)
     e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cuda", seed=seed)
+    e.set_fused_optimizer(fused, keep_grads=True)
     _sync(orc, e)
     return orc, e
 
@@ -81,11 +82,14 @@ def _grads(net):
     return [t.detach().float().cpu().numpy() for t in out]
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("variant,Z,G,B", [("cont", 3, 2000, 128), ("classify", 10, 600, 64),
                                            ("cont", 8, 5, 3), ("cont", 3, 333, 7)])
-def test_every_substep_from_identical_weights(variant, Z, G, B):
+def test_every_substep_from_identical_weights(variant, Z, G, B, fused):
+    """fused: RMSprop inside the wgrad GEMM epilogue (the single-GPU default); not fused: flat
+    gradient buffer + one rmsprop sweep (the data-parallel path)"""
     from cellcomm_b200 import ops
-    orc, e = _setup(variant, Z, G, B)
+    orc, e = _setup(variant, Z, G, B, fused=fused)
     x, z, r = _inputs(variant, Z, G, B, 11)
     masks = O.make_masks(variant, Z, G, B, 3)
     dmasks = _dev_masks(masks)

@@ -27,6 +27,7 @@ def _run(monkeypatch, level, small_width, weights_dtype=torch.bfloat16):
     orc = O.OracleBiGan(variant, Z, G, seed=0, dtype=torch.float32)
     monkeypatch.setattr(ops_emulator, "COMPUTE_DTYPE", weights_dtype)
     e = eng.BiGanEngine(variant, Z, G, max_batch=B, device="cpu", seed=0)
+    e.set_fused_optimizer(True, keep_grads=True)
     monkeypatch.setattr(ops_emulator, "COMPUTE_DTYPE", torch.bfloat16)
     x, z, r = P._inputs(variant, Z, G, B, 11)
     masks = O.make_masks(variant, Z, G, B, 3)
