@@ -66,6 +66,7 @@ struct GemmParams {
   unsigned long long adesc_hi, bdesc_hi;
   unsigned int a_kstep, b_kstep;  // bytes to advance the start address per UMMA_K
   unsigned int idesc;
+  int rms_prefetch;  // fused optimiser: L2-prefetch the next tile's parameter / slot rows
 };
 
 struct TmaMaps {
@@ -212,76 +213,204 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& e, int r, int 
   }
 }
 
-// Epilogue math only (bias, activation, act' multiply) on a thread's 32 columns of row r.
-__device__ __forceinline__ void epilogue_math32(const EpiParams& e, int r, int c0, float (&v)[32]) {
-  const int ncols = min(32, e.N - c0);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = v[j] * e.alpha;
-    if (e.bias != nullptr && j < ncols) x += __ldg(e.bias + c0 + j);
-    if (e.act == CC_ACT_SIGMOID) x = sigmoidf_(x);
-    else if (e.act == CC_ACT_RELU) x = fmaxf(x, 0.f);
-    v[j] = x;
+// Persistent-kernel epilogue for one 32 x 32 block of a warp (thread `lane` holds the raw fp32
+// accumulators of row r0+lane, columns c0..c0+31).  The block is transposed through a padded
+// smem tile (row stride 36 floats: the 16-byte row writes and the 16-byte reads are both
+// bank-conflict free); afterwards lane (rs = lane/8, cg = lane%8) owns columns c0+4cg..+3 of
+// rows rs, rs+4, ..., rs+28, so every global instruction of the warp touches 4 rows x 128
+// contiguous bytes (fp32) and bias / act' operands are loaded once per lane, vectorised.
+// MATH = false strips alpha / bias / activation / act' (wgrad and dgrad tiles).
+constexpr int EPI_LD = 36;
+
+__device__ __forceinline__ float4 act4(float4 v, int act) {
+  if (act == CC_ACT_SIGMOID) {
+    v.x = sigmoidf_(v.x); v.y = sigmoidf_(v.y); v.z = sigmoidf_(v.z); v.w = sigmoidf_(v.w);
+  } else if (act == CC_ACT_RELU) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
   }
-  if (e.dact != 0 && r < e.M) {
-    const bf16* yrow = e.dact_y + (long long)r * e.ld_dact + c0;
+  return v;
+}
+
+template <int K>
+__device__ __forceinline__ float f4c(const float4& v) {
+  return K == 0 ? v.x : (K == 1 ? v.y : (K == 2 ? v.z : v.w));
+}
+template <int K>
+__device__ __forceinline__ void f4set(float4& v, float x) {
+  if (K == 0) v.x = x; else if (K == 1) v.y = x; else if (K == 2) v.z = x; else v.w = x;
+}
+// apply f(t, k, value&) to every valid (row t, column k) of the lane's 8 x 4 block, fully
+// unrolled (no dynamically indexed local arrays -> no stack traffic)
+template <typename F>
+__device__ __forceinline__ void for_each_valid(float4 (&g)[8], int nrow, int ncol, F f) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < ncols) {
-        float y = bf2f(yrow[j]);
-        v[j] *= (e.dact == CC_ACT_SIGMOID) ? y * (1.f - y) : (y > 0.f ? 1.f : 0.f);
-      }
+  for (int t = 0; t < 8; ++t) {
+    if (t < nrow) {
+      if (0 < ncol) f(t, 0, g[t].x);
+      if (1 < ncol) f(t, 1, g[t].y);
+      if (2 < ncol) f(t, 2, g[t].z);
+      if (3 < ncol) f(t, 3, g[t].w);
     }
   }
 }
 
-// Coalesced store of a warp's 32 x 32 block (thread `lane` holds row r0+lane, columns
-// c0..c0+31): transpose through a padded smem tile so that every store instruction writes one
-// contiguous row segment (128 B fp32 / 64 B bf16) instead of 32 scattered 16-byte pieces.
-__device__ __forceinline__ void epilogue_store_coalesced(const EpiParams& e, float* stage /*32x33*/,
-                                                         int lane, int r0, int c0,
-                                                         const float (&v)[32]) {
+template <bool MATH>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage /*32x36*/, int lane,
+                                               int r0, int c0, const uint32_t (&raw)[32]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<uint4*>(stage + lane * EPI_LD + j) =
+        make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
   __syncwarp();
-  const int c = c0 + lane;
-  const bool col_ok = c < e.N;
-  const int rows = min(32, e.M - r0);
-  if (e.rms_p32 != nullptr && col_ok) {
-    // ms = rho*ms + (1-rho) g^2 ; mom = momentum*mom + lr*g/sqrt(ms+eps) ; w -= mom
-    long long off = (long long)r0 * e.rms_ld + c;
-    for (int rr = 0; rr < rows; ++rr, off += e.rms_ld) {
-      const float g = stage[rr * 33 + lane];
-      const float ms = e.rms_rho * e.rms_ms[off] + (1.f - e.rms_rho) * g * g;
-      const float mo = e.rms_momentum * e.rms_mom[off] + e.rms_lr * g * rsqrtf(ms + e.rms_eps);
-      const float w = e.rms_p32[off] - mo;
-      e.rms_ms[off] = ms;
-      e.rms_mom[off] = mo;
-      e.rms_p32[off] = w;
-      if (e.rms_p16 != nullptr) e.rms_p16[off] = f2bf(w);
+  const int rs = lane >> 3, cg = lane & 7;
+  const int c = c0 + 4 * cg;
+  const int ncol = min(4, e.N - c);  // valid columns of this lane's float4 (<= 0: none)
+  float4 g[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    g[t] = *reinterpret_cast<const float4*>(stage + (t * 4 + rs) * EPI_LD + 4 * cg);
+  __syncwarp();  // the tile may be overwritten by the next chunk from here on
+  if (ncol <= 0) return;
+  const int rbase = r0 + rs;               // rows rbase + 4t
+  const int nrow = (e.M - rbase + 3) >> 2;  // number of valid t (may be <= 0 or > 8)
+
+  if (MATH) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias != nullptr) {
+      if (ncol == 4 && ((((uintptr_t)(e.bias + c)) & 15) == 0)) {
+        b4 = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+      } else {
+        b4.x = __ldg(e.bias + c);
+        if (ncol > 1) b4.y = __ldg(e.bias + c + 1);
+        if (ncol > 2) b4.z = __ldg(e.bias + c + 2);
+        if (ncol > 3) b4.w = __ldg(e.bias + c + 3);
+      }
+    }
+    const float al = e.alpha;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      g[t].x = fmaf(g[t].x, al, b4.x);
+      g[t].y = fmaf(g[t].y, al, b4.y);
+      g[t].z = fmaf(g[t].z, al, b4.z);
+      g[t].w = fmaf(g[t].w, al, b4.w);
+      g[t] = act4(g[t], e.act);
+    }
+    if (e.dact != 0) {
+      const bf16* y0 = e.dact_y + (long long)rbase * e.ld_dact + c;
+      const long long ystep = 4 * e.ld_dact;
+      const int dact = e.dact;
+      for_each_valid(g, nrow, ncol, [&](int t, int k, float& x) {
+        const float yy = bf2f(y0[t * ystep + k]);
+        x *= (dact == CC_ACT_SIGMOID) ? yy * (1.f - yy) : (yy > 0.f ? 1.f : 0.f);
+      });
+    }
+  }
+
+  if (e.rms_p32 != nullptr) {
+    // fused Keras RMSprop(momentum): ms = rho*ms + (1-rho) g^2 ; mom = momentum*mom +
+    // lr*g/sqrt(ms+eps) ; w -= mom ; bf16 copy.  All loads are issued before the first use.
+    const bool vec = ncol == 4 && (e.rms_ld & 3) == 0 && ((c & 3) == 0) &&
+                     ((((uintptr_t)e.rms_p32) & 15) == 0) && ((((uintptr_t)e.rms_ms) & 15) == 0) &&
+                     ((((uintptr_t)e.rms_mom) & 15) == 0) &&
+                     (e.rms_p16 == nullptr || (((uintptr_t)e.rms_p16) & 7) == 0);
+    const long long off0 = (long long)rbase * e.rms_ld + c;
+    const long long step = 4 * e.rms_ld;
+    if (vec) {
+      float4 w[8], s[8], m[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < nrow) {
+          const long long off = off0 + t * step;
+          w[t] = *reinterpret_cast<const float4*>(e.rms_p32 + off);
+          s[t] = *reinterpret_cast<const float4*>(e.rms_ms + off);
+          m[t] = *reinterpret_cast<const float4*>(e.rms_mom + off);
+        }
+      }
+      const float rho = e.rms_rho, omr = 1.f - e.rms_rho, mu = e.rms_momentum, lr = e.rms_lr,
+                  eps = e.rms_eps;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < nrow) {
+          const long long off = off0 + t * step;
+          float4 ss, mm, ww;
+          ss.x = rho * s[t].x + omr * g[t].x * g[t].x;
+          ss.y = rho * s[t].y + omr * g[t].y * g[t].y;
+          ss.z = rho * s[t].z + omr * g[t].z * g[t].z;
+          ss.w = rho * s[t].w + omr * g[t].w * g[t].w;
+          mm.x = mu * m[t].x + lr * g[t].x * rsqrtf(ss.x + eps);
+          mm.y = mu * m[t].y + lr * g[t].y * rsqrtf(ss.y + eps);
+          mm.z = mu * m[t].z + lr * g[t].z * rsqrtf(ss.z + eps);
+          mm.w = mu * m[t].w + lr * g[t].w * rsqrtf(ss.w + eps);
+          ww.x = w[t].x - mm.x;
+          ww.y = w[t].y - mm.y;
+          ww.z = w[t].z - mm.z;
+          ww.w = w[t].w - mm.w;
+          *reinterpret_cast<float4*>(e.rms_ms + off) = ss;
+          *reinterpret_cast<float4*>(e.rms_mom + off) = mm;
+          *reinterpret_cast<float4*>(e.rms_p32 + off) = ww;
+          if (e.rms_p16 != nullptr) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(ww.x, ww.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(ww.z, ww.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo);
+            u.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(e.rms_p16 + off) = u;
+          }
+        }
+      }
+    } else {
+      for_each_valid(g, nrow, ncol, [&](int t, int k, float& gv) {
+        const long long off = off0 + t * step + k;
+        const float ms = e.rms_rho * e.rms_ms[off] + (1.f - e.rms_rho) * gv * gv;
+        const float mo = e.rms_momentum * e.rms_mom[off] + e.rms_lr * gv * rsqrtf(ms + e.rms_eps);
+        const float w = e.rms_p32[off] - mo;
+        e.rms_ms[off] = ms;
+        e.rms_mom[off] = mo;
+        e.rms_p32[off] = w;
+        if (e.rms_p16 != nullptr) e.rms_p16[off] = f2bf(w);
+      });
     }
   }
   if (e.out32 != nullptr) {
-    float* o = e.out32 + (long long)r0 * e.ld32 + c;
-    if (e.beta32) {
-      for (int rr = 0; rr < rows; ++rr, o += e.ld32)
-        if (col_ok) *o += stage[rr * 33 + lane];
+    float* o = e.out32 + (long long)rbase * e.ld32 + c;
+    const long long step = 4 * e.ld32;
+    if (ncol == 4 && !e.beta32 && (e.ld32 & 3) == 0 && ((c & 3) == 0) &&
+        ((((uintptr_t)e.out32) & 15) == 0)) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < nrow) *reinterpret_cast<float4*>(o + t * step) = g[t];
     } else {
-      for (int rr = 0; rr < rows; ++rr, o += e.ld32)
-        if (col_ok) *o = stage[rr * 33 + lane];
+      const int beta = e.beta32;
+      for_each_valid(g, nrow, ncol, [&](int t, int k, float& gv) {
+        float* ot = o + t * step + k;
+        *ot = beta ? *ot + gv : gv;
+      });
     }
   }
   if (e.out16 != nullptr) {
-    bf16* o = e.out16 + (long long)r0 * e.ld16 + c;
-    if (e.beta16) {
-      for (int rr = 0; rr < rows; ++rr, o += e.ld16)
-        if (col_ok) *o = f2bf(bf2f(*o) + stage[rr * 33 + lane]);
+    bf16* o = e.out16 + (long long)rbase * e.ld16 + c;
+    const long long step = 4 * e.ld16;
+    if (ncol == 4 && !e.beta16 && (e.ld16 & 3) == 0 && ((c & 3) == 0) &&
+        ((((uintptr_t)e.out16) & 7) == 0)) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < nrow) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(g[t].x, g[t].y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(g[t].z, g[t].w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&lo);
+          u.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(o + t * step) = u;
+        }
+      }
     } else {
-      for (int rr = 0; rr < rows; ++rr, o += e.ld16)
-        if (col_ok) *o = f2bf(stage[rr * 33 + lane]);
+      const int beta = e.beta16;
+      for_each_valid(g, nrow, ncol, [&](int t, int k, float& gv) {
+        bf16* ot = o + t * step + k;
+        *ot = f2bf(beta ? bf2f(*ot) + gv : gv);
+      });
     }
   }
-  __syncwarp();
 }
 
 // ------------------------------------------------------------------- kernel
@@ -441,12 +570,26 @@ gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
 // warps 2-5 = epilogue.  The fp32 accumulator is double-buffered in TMEM (2 x BN columns), so
 // the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring has STAGES
 // k-blocks in flight across tile boundaries.
+// Warm L2 with the NEXT tile's optimiser operands (fused RMSprop epilogue): one thread walks
+// the consecutive 128-byte lines of its row, so DRAM sees page-local bursts instead of the
+// scattered 128-byte demand reads of the chunked epilogue.
+__device__ __forceinline__ void rms_prefetch_row(const EpiParams& e, int r, int c_lo, int ncols) {
+  if (e.rms_p32 == nullptr || r >= e.M || c_lo >= e.N) return;
+  const long long off = (long long)r * e.rms_ld + c_lo;
+  const int n = min(ncols, e.N - c_lo);
+  for (int i = 0; i < n; i += 32) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_p32 + off + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_ms + off + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_mom + off + i));
+  }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p,
                                const int tiles_m, const int tiles_n) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -467,7 +610,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 4));
   // per-epilogue-warp 32x33 fp32 transpose tiles, after the barrier block
-  float* epi_stage = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 6));
+  float* epi_stage = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 6));  // 16-B aligned: 2*STAGES+6 is even
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -483,7 +626,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -566,28 +709,37 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
       }
     }
   } else {
-    // ===================== epilogue warps 2..5 =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps 2.. =====================
+    // TMEM lane quarter = warp id mod 4 (hardware rule); with 8 epilogue warps the two warps of
+    // a quarter split the tile's columns (more loads in flight for the fused optimiser)
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+    const int col_lo = (ew >> 2) * COLS_PER_WARP;
     uint32_t tl = 0;
+    const bool do_pf = p.epi.rms_p32 != nullptr && p.rms_prefetch != 0;
+    if (do_pf && (int)blockIdx.x < num_tiles)
+      rms_prefetch_row(p.epi, (blockIdx.x % tiles_m) * BM + q * 32 + lane,
+                       (blockIdx.x / tiles_m) * BN + col_lo, COLS_PER_WARP);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int m0 = (tile % tiles_m) * BM;
       const int n0 = (tile / tiles_m) * BN;
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      if (do_pf && tile + (int)gridDim.x < num_tiles) {
+        const int nxt = tile + gridDim.x;
+        rms_prefetch_row(p.epi, (nxt % tiles_m) * BM + q * 32 + lane,
+                         (nxt / tiles_m) * BN + col_lo, COLS_PER_WARP);
+      }
       mbar_wait(tfull_bar(acc), aph, 14);
       tcgen05_fence_after();
-      const int r = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = col_lo; c < col_lo + COLS_PER_WARP; c += 32) {
         if (n0 + c >= p.epi.N) break;  // warp-uniform
         uint32_t raw[32];
         tmem_ld32(t_row + (uint32_t)c, raw);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        epilogue_math32(p.epi, r, n0 + c, v);
-        epilogue_store_coalesced(p.epi, epi_stage + q * (32 * 33), lane, m0 + q * 32, n0 + c, v);
+        epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -752,35 +904,45 @@ static int launch_major(const TmaMaps& maps, const GemmParams& p, dim3 grid, boo
   return launch_cfg<BN, STAGES, true, false>(maps, p, grid, st);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI_WARPS>
 static constexpr size_t smem_bytes_persistent() {
-  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 6) + 4 * 32 * 33 * 4 + 1024;
+  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 6) + 16 +
+         EPI_WARPS * 32 * EPI_LD * 4 + 1024;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS = 4>
 static int launch_persistent_cfg(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
-  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS>;
   static bool attr_set = false;
-  constexpr size_t smem = smem_bytes_persistent<BN, STAGES>();
+  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS>();
   if (!attr_set) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int tiles = mt * nt;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 192, smem, st>>>(maps, p, mt, nt);
+  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(maps, p, mt, nt);
   CC_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, int STAGES, bool MATH>
+static int launch_persistent_m(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
+                               int num_sms, bool a_mn, bool b_mn, cudaStream_t st) {
+  if (!a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, false, true, MATH>(maps, p, mt, nt, num_sms, st);
+  if (!a_mn && !b_mn) return launch_persistent_cfg<BN, STAGES, false, false, MATH>(maps, p, mt, nt, num_sms, st);
+  if (a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, true, true, MATH>(maps, p, mt, nt, num_sms, st);
+  return launch_persistent_cfg<BN, STAGES, true, false, MATH>(maps, p, mt, nt, num_sms, st);
 }
 
 template <int BN, int STAGES>
 static int launch_persistent(const TmaMaps& maps, const GemmParams& p, int mt, int nt, int num_sms,
                              bool a_mn, bool b_mn, cudaStream_t st) {
-  if (!a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, false, true>(maps, p, mt, nt, num_sms, st);
-  if (!a_mn && !b_mn) return launch_persistent_cfg<BN, STAGES, false, false>(maps, p, mt, nt, num_sms, st);
-  if (a_mn && b_mn) return launch_persistent_cfg<BN, STAGES, true, true>(maps, p, mt, nt, num_sms, st);
-  return launch_persistent_cfg<BN, STAGES, true, false>(maps, p, mt, nt, num_sms, st);
+  const EpiParams& e = p.epi;
+  const bool math = e.alpha != 1.f || e.bias != nullptr || e.act != 0 || e.dact != 0;
+  if (math) return launch_persistent_m<BN, STAGES, true>(maps, p, mt, nt, num_sms, a_mn, b_mn, st);
+  return launch_persistent_m<BN, STAGES, false>(maps, p, mt, nt, num_sms, a_mn, b_mn, st);
 }
 
 static int g_num_sms = 0;
@@ -826,6 +988,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     if (rc) return rc;
   }
   p.total_kblocks = total;
+  p.rms_prefetch = env_int("CC_GEMM_RMS_PREFETCH", 1);
 
   // UMMA descriptors.  K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=16B),
   // K advance = 32 B inside the swizzle row.  MN-major, 128B swizzle: 64-element MN atoms are
@@ -904,6 +1067,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   }
 
   if (splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr)) {
+    // fused optimiser on weight gradients (both operands MN-major, no epilogue math): the
+    // epilogue streams 26 B per element, so it gets 8 warps (twice the loads in flight) and
+    // the main loop one stage less
+    if (bn == 256 && d->rms_p32 != nullptr && a_mn && b_mn && d->alpha == 1.f &&
+        d->bias == nullptr && d->act == 0 && e.dact == 0 && env_int("CC_GEMM_RMS_WARPS", 8) == 8)
+      return launch_persistent_cfg<256, 3, true, true, false, 8>(maps, p, mt, nt, g_num_sms, st);
     if (bn == 256) return launch_persistent<256, 4>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
     return launch_persistent<128, 6>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
   }
