@@ -246,10 +246,20 @@ def run_ours(args):
     x16 = ops.alloc2d(B, args.genes, device=dev)
     e.reserve(B)
 
-    def resident_step(i):
+    graphed = None
+    if args.graph and world == 1:
+        graphed = e.capture_step((rowptr, colidx, values), args.genes, B, latents="device")
+
+    def eager_step(i):
         ops.gather_rows(rowptr, colidx, values, args.genes, row_idx=idx_all[i], out16=x16)
         e.draw_latents(B)
         return e.train_step(x16)
+
+    def resident_step(i):
+        if graphed is not None:
+            graphed.idx.copy_(idx_all[i], non_blocking=True)
+            return graphed.replay()
+        return eager_step(i)
 
     for i in range(args.warmup):
         resident_step(i)
@@ -266,6 +276,8 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = ops.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps
     ms_resident = max_over_ranks(ev0.elapsed_time(ev1))
     last_losses = [float(v) for v in losses]
 
@@ -321,25 +333,41 @@ def run_ours(args):
         real_gemm = ops.gemm
         pairs = []
 
+        shapes = []
+
         def timed_gemm(*a, **k):
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             real_gemm(*a, **k)
             t.record()
             pairs.append((s, t))
+            shapes.append((a[0], a[1], tuple(a[4]), a[5], a[6]))
 
         ops.gemm = timed_gemm
         try:
             reps = 2
             ev0.record()
             for i in range(reps):
-                resident_step(i)
+                eager_step(i)
             e.join()
             ev1.record()
             torch.cuda.synchronize()
             inst_ms = ev0.elapsed_time(ev1) / reps
             gemm_total = sum(s.elapsed_time(t) for s, t in pairs) / reps
             gemm_ms = [gemm_total, len(pairs) // reps, inst_ms]
+            table_path = os.environ.get("CELLCOMM_BENCH_GEMM_TABLE")
+            if table_path:
+                agg = {}
+                for (s_, t_), sh in zip(pairs, shapes):
+                    rec = agg.setdefault(sh, [0, 0.0])
+                    rec[0] += 1
+                    rec[1] += s_.elapsed_time(t_)
+                rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+                with open(table_path, "w") as f:
+                    for (M_, N_, ks, am, bm), (n, ms) in rows:
+                        fl = 2.0 * M_ * N_ * sum(ks) * n
+                        f.write(f"{ms / reps:8.3f} ms/step  n={n // reps:3d}  M={M_:6d} N={N_:6d} "
+                                f"K={ks} a_mn={am} b_mn={bm}  {fl / ms / 1e9:7.1f} TFLOP/s\n")
         finally:
             ops.gemm = real_gemm
     if world > 1:
@@ -390,6 +418,7 @@ def run_ours(args):
             (peak_tf * world), "d2h_bytes": args.cells * Z * 4,
         },
         "losses_last_step": last_losses, "setup_seconds": setup_s,
+        "cuda_graph": bool(graphed is not None),
         "precision_policy": "bf16 GEMM operands, fp32 accumulate; fp32 master weights + RMSprop "
                             "slots; CELLCOMM_B200_SPLIT=" + os.environ.get("CELLCOMM_B200_SPLIT", "auto"),
     }
@@ -418,6 +447,8 @@ def main():
     ap.add_argument("--encode-tile", type=int, default=4096)
     ap.add_argument("--encode-reps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("CELLCOMM_BENCH_GRAPH", "1")),
+                    help="1: run the device-resident loop as one CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

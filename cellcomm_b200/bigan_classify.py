@@ -121,6 +121,14 @@ class ClassifyCellBiGan(BasicBiGan):
         batch_size = len(batch)
         encodings = self.random_encoding_vector(batch_size)
         noise = self.random_uniform_vector(batch_size)
+        if (isinstance(batch, CellBatch) and eng.device.type == "cuda" and
+                eng.dist.world_size == 1 and os.environ.get("CELLCOMM_B200_GRAPH", "1") != "0"):
+            # single GPU: the whole step (gather + ~850 kernels) is one CUDA-graph launch
+            gs = eng.capture_step(batch.matrix.device_csr(eng.device), batch.matrix.shape[1],
+                                  batch_size, latents="host")
+            eng.z32[:batch_size].copy_(_as_f32(encodings), non_blocking=True)
+            eng.r32[:batch_size].copy_(_as_f32(noise), non_blocking=True)
+            return gs.replay(batch.positions)
         x16 = self._stage_cells(batch)
         eng.set_latents(encodings, noise, batch_size)
         g_loss, e_loss, d_loss = eng.train_step(x16)
@@ -240,6 +248,11 @@ class ClassifyCellBiGan(BasicBiGan):
         eng.substep(substep, cells)
         slot = {1: 0, 2: 1, 3: 2, 4: 3, 6: 4, 8: 5}[substep]
         return float(eng.loss_buf[slot])
+
+
+def _as_f32(a):
+    import torch
+    return torch.as_tensor(np.asarray(a, dtype=np.float32))
 
 
 def _sliceable(x):

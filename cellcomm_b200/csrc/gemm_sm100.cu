@@ -1040,10 +1040,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   if (d->workspace != nullptr && d->rms_p32 == nullptr) {
     int want = d->force_splits ? d->force_splits : env_int("CC_GEMM_SPLITS", 0);
     if (want == 0) {
+      // split-K only when the tile grid leaves more than half of the SMs idle (small batch,
+      // long reduction: the weight-streaming regime of the reference's batch 128); otherwise
+      // the persistent kernel runs the tiles unsplit
       const int tiles = mt * nt;
-      const int slots = 2 * g_num_sms;
-      if (tiles < slots && total >= 8) {
-        want = (slots + tiles - 1) / tiles;
+      if (2 * tiles <= g_num_sms && total >= 8) {
+        want = (2 * g_num_sms + tiles - 1) / tiles;
         if (want > total / 4) want = total / 4;
       } else {
         want = 1;

@@ -894,7 +894,17 @@ extern "C" int cc_rmsprop_step(float* p32, void* p16, const float* g, float* ms,
                                float momentum, float eps, float grad_scale, cc_stream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
   const long long work = (long long)rows * ((cols + 3) / 4);
-  rmsprop_kernel<<<ew_grid(work, 256), 256, 0, ST(stream)>>>(p32, (bf16*)p16, g, ms, mom, rows,
+  // CC_RMS_BLOCKS_PER_SM (default 8 = full occupancy): a smaller value leaves thread slots for
+  // GEMM CTAs when the sweep runs on the side stream next to the following forward pass
+  static int bps = 0;
+  if (bps == 0) {
+    const char* v = getenv("CC_RMS_BLOCKS_PER_SM");
+    bps = v ? atoi(v) : 8;
+    if (bps < 1 || bps > 8) bps = 8;
+  }
+  long long blocks = (work + 255) / 256;
+  if (blocks > (long long)num_sms() * bps) blocks = (long long)num_sms() * bps;
+  rmsprop_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(p32, (bf16*)p16, g, ms, mom, rows,
                                                              cols, ld, lr, rho, momentum, eps,
                                                              grad_scale);
   CC_CHECK_LAUNCH();

@@ -833,6 +833,56 @@ class LossScalar:
         return id(self)
 
 
+class GraphedStep:
+    """One trainings_step on `batch` rows captured as a CUDA graph (see capture_step)."""
+
+    def __init__(self, eng, csr, n_cols, batch, latents):
+        self.eng, self.batch, self.latents = eng, int(batch), latents
+        rowptr, colidx, values = csr
+        dev = eng.device
+        eng.reserve(batch)
+        self.idx = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.x16 = ops.alloc2d(batch, n_cols, device=dev)
+        saved = [(n, n.opt_stream) for n in eng.nets.values()]
+        for n, _ in saved:                       # no side streams inside the capture
+            n._wait_optimizer()
+            n.opt_stream = None
+
+        def body():
+            ops.gather_rows(rowptr, colidx, values, n_cols, row_idx=self.idx, out16=self.x16)
+            if latents == "device":
+                eng.draw_latents(batch)
+            else:
+                ops.cast_f32_to_bf16(eng.z32[:batch], eng.z16[:batch])
+                ops.cast_f32_to_bf16(eng.r32[:batch], eng.r16[:batch])
+            return eng.train_step(self.x16)
+
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):        # warm-up: buffers, kernel attributes, tensor maps
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.losses = body()
+            # kernels of libcellcomm_b200.so captured in the graph (each replay runs them all)
+            self.launches_per_replay = ops.launch_count() - l0
+        finally:
+            for n, st in saved:
+                n.opt_stream = st
+
+    def replay(self, idx=None):
+        """idx: batch row positions (host or device int64); None keeps the current buffer."""
+        if idx is not None:
+            self.idx.copy_(torch.as_tensor(idx), non_blocking=True)
+        self.graph.replay()
+        return self.losses
+
+
 class BiGanEngine:
     """G, E, D plus the eight sub-steps of `trainings_step` (src/bigan_classify.py:126-155)."""
 
@@ -877,6 +927,7 @@ class BiGanEngine:
         self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.max_batch = 0
+        self._graphs = {}
         self.reserve(max_batch)
 
     def set_fused_optimizer(self, on, keep_grads=False):
@@ -892,6 +943,7 @@ class BiGanEngine:
         rows = int(rows)
         if rows <= self.max_batch:
             return
+        self._graphs = {}              # captured steps hold pointers into the old buffers
         self.max_batch = mb = rows
         Z, dev = self.Z, self.device
         for n in self.nets.values():
@@ -1033,6 +1085,28 @@ class BiGanEngine:
         d = LossScalar((Lc[4] + Lc[5]) * 0.5)       # np.mean([d_loss_1, d_loss_2])    :140
         self.last_losses = Lc
         return g, e, d
+
+    # ------------------------------------------------------------------ CUDA graph of a step
+    def capture_step(self, csr, n_cols, batch, latents="device"):
+        """Capture gather -> (priors) -> trainings_step for a fixed batch size into ONE CUDA
+        graph (~850 kernel launches become one graph launch; at the reference's batch of 128 the
+        eager step is bound by host launch overhead, not by the GPU).
+
+        csr = (rowptr, colidx, values) on the device.  latents = "device": tf.random.uniform
+        priors are drawn inside the graph from the Philox streams; "host": the caller writes
+        self.z32 / self.r32 before every replay.  Returns GraphedStep; .idx is the static row
+        index buffer to fill before .replay()."""
+        if self.device.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        if self.dist.world_size > 1:
+            raise RuntimeError("graph capture is single-GPU (collectives are not captured)")
+        self.reserve(batch)
+        key = (int(batch), latents, csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr())
+        gs = self._graphs.get(key)
+        if gs is None:
+            gs = GraphedStep(self, csr, n_cols, batch, latents)
+            self._graphs[key] = gs
+        return gs
 
     # ------------------------------------------------------------------ inference
     def encode(self, x16, out32=None):

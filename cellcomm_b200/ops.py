@@ -153,8 +153,10 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None):
     K, N = (dw32.shape if dw32 is not None else rms[0].shape)
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
-    gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta, use_ws=False,
-         rms=rms)
+    # tiny layers (one or two output tiles, reduction over the whole batch) take the split-K
+    # path; the fused-optimiser epilogue cannot be split
+    gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta,
+         use_ws=rms is None, rms=rms)
 
 
 # --------------------------------------------------------------------------- data

@@ -214,3 +214,51 @@ def test_rng_mode_trains():
         losses.append((float(g), float(ee), float(d)))
     assert all(np.isfinite(v) for t in losses for v in t)
     assert int(e.rng_counter.item()) == 3
+
+
+def test_cuda_graph_step_matches_eager():
+    """capture_step: the whole trainings_step as one CUDA graph gives the eager losses"""
+    import numpy as np
+    from cellcomm_b200 import engine as eng, ops
+    from cellcomm_b200.cell_type_training import CellMatrix
+    B, G, N = 64, 700, 300
+    rng = np.random.default_rng(0)
+    dense = (rng.random((N, G)) < 0.06) * (rng.poisson(1.2, (N, G)) + 1)
+    data = CellMatrix.from_dense(dense.astype(np.float64))
+    csr = data.device_csr("cuda")
+    idx = torch.from_numpy(np.random.RandomState(0).permutation(N)[:B]).cuda()
+    z, r = torch.rand(B, 3), torch.rand(B, 3)
+    out = []
+    for graphed in (False, True):
+        e = eng.BiGanEngine("cont", 3, G, max_batch=B, device="cuda", seed=5)
+        e.rng_seed = 1234                      # same dropout streams in both runs
+        losses = []
+        if graphed:
+            gs = e.capture_step(csr, G, B, latents="host")
+            w0 = None
+        for step in range(3):
+            if graphed and step == 0:
+                # capture ran warm-up steps: restart from the same weights as the eager run
+                e2 = eng.BiGanEngine("cont", 3, G, max_batch=B, device="cuda", seed=5)
+                for n in ("G", "E", "D"):
+                    e.nets[n].set_weights(e2.nets[n].get_weights())
+                    e.nets[n].set_slots(e2.nets[n].get_slots())
+                    for La, Lb in zip(e.nets[n].layers, e2.nets[n].layers):
+                        if La["kind"] == "bn":
+                            La["moving_mean"].copy_(Lb["moving_mean"])
+                            La["moving_var"].copy_(Lb["moving_var"])
+                e.rng_counter.zero_()
+            if graphed:
+                e.z32[:B].copy_(z)
+                e.r32[:B].copy_(r)
+                l = gs.replay(idx)
+            else:
+                x16 = ops.alloc2d(B, G)
+                ops.gather_rows(*csr, G, row_idx=idx, out16=x16)
+                e.set_latents(z, r, B)
+                l = e.train_step(x16)
+            losses.append([float(v) for v in l])
+        out.append(losses)
+    for a, b in zip(out[0], out[1]):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-3 * abs(y) + 1e-4, (out[0], out[1])
