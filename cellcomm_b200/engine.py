@@ -247,6 +247,7 @@ class Net:
         # next network's forward pass; every use of this net's parameters waits for the event
         self.opt_stream = None
         self._opt_event = None
+        self.on_grow = None
         self.fuse_optimizer = False   # kernels updated inside the wgrad epilogue (1 GPU)
         self.keep_grads = False       # fused mode: also write dW (parity tests)
         self.hp, self.split = self._high_precision_tensors()
@@ -438,6 +439,8 @@ class Net:
     def reserve(self, rows):
         """Grow the activation/gradient buffers to hold `rows` rows (drops the old ones)."""
         if rows > self.max_rows:
+            if self.on_grow is not None:
+                self.on_grow()      # captured CUDA graphs point into the buffers dropped below
             self.max_rows = int(rows)
             self.act, self.grad, self.tmp, self.shadow, self.dzb = {}, {}, {}, {}, {}
             self.split_lo = {}
@@ -858,12 +861,17 @@ class GraphedStep:
             return eng.train_step(self.x16)
 
         try:
+            # warm-up run (allocates lazy buffers, sets kernel attributes, fills the tensor-map
+            # cache) on a side stream as torch requires; it is a real training step, so the
+            # model / optimiser / RNG state is snapshotted and restored around it
+            snap = eng.snapshot_state()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):        # warm-up: buffers, kernel attributes, tensor maps
-                for _ in range(2):
-                    body()
+            with torch.cuda.stream(side):
+                body()
             torch.cuda.current_stream().wait_stream(side)
+            eng.restore_state(snap)
+            del snap
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             l0 = ops.launch_count()
@@ -913,6 +921,9 @@ class BiGanEngine:
         self.E = Net(graphs["E"], max_batch, self.device, gen, self.dist)
         self.D = Net(graphs["D"], max_batch, self.device, gen, self.dist)
         self.nets = {"G": self.G, "E": self.E, "D": self.D}
+        self._graphs = {}
+        for n in self.nets.values():
+            n.on_grow = self._graphs.clear
         # default: flat RMSprop sweeps on a side stream, overlapped with the next network's
         # forward (measured faster than the fused wgrad epilogue, which streams the optimiser
         # state at ~3.5 TB/s against the sweep's 5.5-5.8 TB/s); CELLCOMM_B200_FUSE_OPT=1 selects
@@ -927,7 +938,6 @@ class BiGanEngine:
         self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.max_batch = 0
-        self._graphs = {}
         self.reserve(max_batch)
 
     def set_fused_optimizer(self, on, keep_grads=False):
@@ -943,7 +953,7 @@ class BiGanEngine:
         rows = int(rows)
         if rows <= self.max_batch:
             return
-        self._graphs = {}              # captured steps hold pointers into the old buffers
+        self._graphs.clear()           # captured steps hold pointers into the old buffers
         self.max_batch = mb = rows
         Z, dev = self.Z, self.device
         for n in self.nets.values():
@@ -1067,6 +1077,31 @@ class BiGanEngine:
             D.apply_rmsprop()
         else:
             raise ValueError(f"no sub-step {k}")
+
+    def snapshot_state(self):
+        """Device copies of everything a training step mutates (weights, bf16 copies, RMSprop
+        slots, BN moving statistics, RNG counter)."""
+        self.join()
+        snap = {"rng": self.rng_counter.clone()}
+        for k, n in self.nets.items():
+            snap[k] = {"p32": n.p32.clone(), "p16": n.p16.clone(), "ms": n.ms.clone(),
+                       "mom": n.mom.clone(),
+                       "bn": [(L["moving_mean"].clone(), L["moving_var"].clone())
+                              for L in n.layers if L["kind"] == "bn"]}
+        return snap
+
+    def restore_state(self, snap):
+        self.join()
+        self.rng_counter.copy_(snap["rng"])
+        for k, n in self.nets.items():
+            s = snap[k]
+            n.p32.copy_(s["p32"])
+            n.p16.copy_(s["p16"])
+            n.ms.copy_(s["ms"])
+            n.mom.copy_(s["mom"])
+            for L, (mm, mv) in zip([L for L in n.layers if L["kind"] == "bn"], s["bn"]):
+                L["moving_mean"].copy_(mm)
+                L["moving_var"].copy_(mv)
 
     def join(self):
         """Order the current stream after every pending side-stream optimiser update (call

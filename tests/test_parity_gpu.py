@@ -234,20 +234,8 @@ def test_cuda_graph_step_matches_eager():
         e.rng_seed = 1234                      # same dropout streams in both runs
         losses = []
         if graphed:
-            gs = e.capture_step(csr, G, B, latents="host")
-            w0 = None
+            gs = e.capture_step(csr, G, B, latents="host")   # must leave the state untouched
         for step in range(3):
-            if graphed and step == 0:
-                # capture ran warm-up steps: restart from the same weights as the eager run
-                e2 = eng.BiGanEngine("cont", 3, G, max_batch=B, device="cuda", seed=5)
-                for n in ("G", "E", "D"):
-                    e.nets[n].set_weights(e2.nets[n].get_weights())
-                    e.nets[n].set_slots(e2.nets[n].get_slots())
-                    for La, Lb in zip(e.nets[n].layers, e2.nets[n].layers):
-                        if La["kind"] == "bn":
-                            La["moving_mean"].copy_(Lb["moving_mean"])
-                            La["moving_var"].copy_(Lb["moving_var"])
-                e.rng_counter.zero_()
             if graphed:
                 e.z32[:B].copy_(z)
                 e.r32[:B].copy_(r)
