@@ -35,6 +35,8 @@ _ACT = {"none": 0, "sigmoid": 1, "relu": 2, "softmax": 0}
 _SPLIT_ENV = os.environ.get("CELLCOMM_B200_SPLIT", "auto")
 _SPLIT_PRECISION = None if _SPLIT_ENV == "auto" else int(_SPLIT_ENV)
 _SMALL_WIDTH = int(os.environ.get("CELLCOMM_B200_SMALL_WIDTH", "512"))
+# data parallel: reduce-scatter + sharded RMSprop + bf16 all-gather instead of all-reduce + full sweep
+_SHARD_OPTIMIZER = os.environ.get("CELLCOMM_B200_SHARD_OPT", "1") != "0"
 
 
 # =========================================================================== graph specs
@@ -214,6 +216,25 @@ class TorchDist:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def reduce_scatter(self, out_shard, full):
+        """out_shard = this rank's 1/world slice of sum_over_ranks(full)."""
+        if self._dist.get_backend(self.group) == "nccl":
+            self._dist.reduce_scatter_tensor(out_shard, full, op=self._dist.ReduceOp.SUM,
+                                             group=self.group)
+        else:   # gloo (CPU tests) has no reduce-scatter: all-reduce and slice
+            self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
+            n = out_shard.numel()
+            out_shard.copy_(full[self.rank * n:(self.rank + 1) * n])
+
+    def all_gather(self, full, shard):
+        """full = concat over ranks of `shard` (shard may be the matching slice of full)."""
+        if self._dist.get_backend(self.group) == "nccl":
+            self._dist.all_gather_into_tensor(full, shard, group=self.group)
+        else:
+            parts = [torch.empty_like(shard) for _ in range(self.world_size)]
+            self._dist.all_gather(parts, shard.clone(), group=self.group)
+            full.copy_(torch.cat(parts))
+
 
 def default_dist():
     """TorchDist when a process group is initialised (torchrun), else single-process."""
@@ -248,6 +269,8 @@ class Net:
         self.opt_stream = None
         self._opt_event = None
         self.on_grow = None
+        self._gshard = None
+        self._master_stale = False
         self.fuse_optimizer = False   # kernels updated inside the wgrad epilogue (1 GPU)
         self.keep_grads = False       # fused mode: also write dW (parity tests)
         self.hp, self.split = self._high_precision_tensors()
@@ -273,6 +296,7 @@ class Net:
                 off += K * ldn
             else:
                 meta.append({"kind": "bn", "n": lay[1]})
+        off = (off + 4095) // 4096 * 4096     # kernel region: shardable across up to 16 ranks
         self.small_off = off
         for m in meta:
             if m["kind"] == "dense":
@@ -281,7 +305,8 @@ class Net:
             else:
                 m["g_off"], m["be_off"] = off, off + _pad(m["n"])
                 off += 2 * _pad(m["n"])
-        self.n_flat = max(off, 64)
+        # padded so that 1/world shards (world <= 16) stay 256-element aligned
+        self.n_flat = max((off + 4095) // 4096 * 4096, 4096)
         self.p32 = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
         self.g32 = torch.zeros_like(self.p32)
         self.ms = torch.zeros_like(self.p32)
@@ -336,6 +361,7 @@ class Net:
     def get_weights(self):
         """Creation order; Dense -> kernel[in,out], bias; BN -> gamma, beta, mean, var (host)."""
         self._wait_optimizer()
+        self.gather_master()
         out = []
         for L in self.layers:
             keys = ("w32", "b32") if L["kind"] == "dense" else (
@@ -759,18 +785,50 @@ class Net:
                                  self.mom[sl], LR, RHO, MOMENTUM, EPSILON)
             return
         if self.opt_stream is None:
-            self.dist.all_reduce(self.g32)
-            ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
-                             EPSILON)
+            self._reduce_and_update()
             return
         main = torch.cuda.current_stream()
         self.opt_stream.wait_stream(main)           # gradients are complete
         with torch.cuda.stream(self.opt_stream):
+            self._reduce_and_update()
+            self._opt_event = torch.cuda.Event()
+            self._opt_event.record(self.opt_stream)
+
+    def _reduce_and_update(self):
+        """Data-parallel update.  world == 1: one sweep.  world > 1 (ZeRO-1 style): reduce-scatter
+        the fp32 gradient, RMSprop on this rank's 1/world shard of the flat buffers (1/world of
+        the 30 B/parameter optimiser traffic), all-gather the bf16 compute copy.  The fp32
+        master copy is then only current on its owner shard; gather_master() refreshes it."""
+        W = self.dist.world_size
+        K = self.small_off                      # Dense kernels: [0, K); biases + BN: [K, n_flat)
+        if W == 1 or not _SHARD_OPTIMIZER or K == 0 or K % (W * 256) != 0:
             self.dist.all_reduce(self.g32)
             ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
                              EPSILON)
-            self._opt_event = torch.cuda.Event()
-            self._opt_event.record(self.opt_stream)
+            return
+        n = K // W
+        sl = slice(self.dist.rank * n, (self.dist.rank + 1) * n)
+        if self._gshard is None:
+            self._gshard = torch.empty(n, dtype=torch.float32, device=self.device)
+        self.dist.reduce_scatter(self._gshard, self.g32[:K])
+        ops.rmsprop_step(self.p32[sl], self.p16[sl], self._gshard, self.ms[sl], self.mom[sl], LR,
+                         RHO, MOMENTUM, EPSILON)
+        self.dist.all_gather(self.p16[:K], self.p16[sl])
+        # biases and BN gamma/beta are read in fp32 by the forward kernels: replicated update
+        tail = slice(K, self.n_flat)
+        self.dist.all_reduce(self.g32[tail])
+        ops.rmsprop_step(self.p32[tail], self.p16[tail], self.g32[tail], self.ms[tail],
+                         self.mom[tail], LR, RHO, MOMENTUM, EPSILON)
+        self._master_stale = True
+
+    def gather_master(self):
+        """Make the fp32 master weights current on every rank (sharded-optimiser runs)."""
+        if self._master_stale and self.dist.world_size > 1:
+            W = self.dist.world_size
+            n = self.small_off // W
+            sl = slice(self.dist.rank * n, (self.dist.rank + 1) * n)
+            self.dist.all_gather(self.p32[:self.small_off], self.p32[sl].clone())
+        self._master_stale = False
 
     def _wait_optimizer(self):
         """Order the current stream after a pending side-stream update of this net."""

@@ -29,6 +29,11 @@ for step in range(3):
 e.join()
 torch.cuda.synchronize()
 for name, n in e.nets.items():
+    c16 = n.p16.clone()
+    r16 = c16.clone()
+    dist.broadcast(r16, src=0)
+    assert torch.equal(c16, r16), f"rank {rank}: {name} bf16 compute copies differ from rank 0"
+    n.gather_master()          # sharded optimiser: fp32 master is current only on its owner
     mine = n.p32.clone()
     ref = mine.clone()
     dist.broadcast(ref, src=0)
