@@ -51,6 +51,7 @@ struct EpiParams {
   bf16* rms_p16;
   long long rms_ld;
   float rms_lr, rms_rho, rms_momentum, rms_eps;
+  int rms_cs;  // evict-first (ld/st.global.cs) hints on the optimiser state stream
 };
 
 struct GemmParams {
@@ -67,6 +68,12 @@ struct GemmParams {
   unsigned int a_kstep, b_kstep;  // bytes to advance the start address per UMMA_K
   unsigned int idesc;
   int rms_prefetch;  // fused optimiser: L2-prefetch the next tile's parameter / slot rows
+  // persistent kernel: effective tile width (multiple of 32, <= BN).  The smem / TMEM layout
+  // stays BN wide; a narrower MMA N trades a little per-tile efficiency for a tile count that
+  // fills the last wave (N = 3369 at BN 256 is 1.51 waves, at 192 it is 1.95).
+  int bn_eff;
+  int b_boxes;            // MN-major B: 64-column TMA boxes per stage
+  unsigned int stage_tx;  // bytes TMA delivers per stage
 };
 
 struct TmaMaps {
@@ -321,9 +328,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
       for (int t = 0; t < 8; ++t) {
         if (t < nrow) {
           const long long off = off0 + t * step;
-          w[t] = *reinterpret_cast<const float4*>(e.rms_p32 + off);
-          s[t] = *reinterpret_cast<const float4*>(e.rms_ms + off);
-          m[t] = *reinterpret_cast<const float4*>(e.rms_mom + off);
+          if (e.rms_cs) {
+            w[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_p32 + off));
+            s[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_ms + off));
+            m[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_mom + off));
+          } else {
+            w[t] = *reinterpret_cast<const float4*>(e.rms_p32 + off);
+            s[t] = *reinterpret_cast<const float4*>(e.rms_ms + off);
+            m[t] = *reinterpret_cast<const float4*>(e.rms_mom + off);
+          }
         }
       }
       const float rho = e.rms_rho, omr = 1.f - e.rms_rho, mu = e.rms_momentum, lr = e.rms_lr,
@@ -345,9 +358,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
           ww.y = w[t].y - mm.y;
           ww.z = w[t].z - mm.z;
           ww.w = w[t].w - mm.w;
-          *reinterpret_cast<float4*>(e.rms_ms + off) = ss;
-          *reinterpret_cast<float4*>(e.rms_mom + off) = mm;
-          *reinterpret_cast<float4*>(e.rms_p32 + off) = ww;
+          if (e.rms_cs) {
+            __stcs(reinterpret_cast<float4*>(e.rms_ms + off), ss);
+            __stcs(reinterpret_cast<float4*>(e.rms_mom + off), mm);
+            __stcs(reinterpret_cast<float4*>(e.rms_p32 + off), ww);
+          } else {
+            *reinterpret_cast<float4*>(e.rms_ms + off) = ss;
+            *reinterpret_cast<float4*>(e.rms_mom + off) = mm;
+            *reinterpret_cast<float4*>(e.rms_p32 + off) = ww;
+          }
           if (e.rms_p16 != nullptr) {
             __nv_bfloat162 lo = __floats2bfloat162_rn(ww.x, ww.y);
             __nv_bfloat162 hi = __floats2bfloat162_rn(ww.z, ww.w);
@@ -588,7 +607,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS>
+// N_FAST: consecutive tiles walk along N (the contiguous direction of the output / parameter
+// matrix), so the CTAs of one wave cover whole output rows: used by the fused-optimiser wgrad,
+// whose epilogue streams 26 B per element and wants DRAM-page-local bursts.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p,
                                const int tiles_m, const int tiles_n) {
@@ -646,8 +668,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
     // ===================== TMA producer =====================
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * BN;
+      const int m0 = (N_FAST ? tile / tiles_n : tile % tiles_m) * BM;
+      const int n0 = (N_FAST ? tile % tiles_n : tile / tiles_m) * p.bn_eff;
       int seg = 0, kb_in_seg = 0;
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % STAGES;
@@ -657,7 +679,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb_in_seg * BK;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), p.stage_tx);
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
@@ -668,7 +690,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
+              if (j < p.b_boxes)
+                tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
           } else {
             tma_load_2d(b_dst, &maps.b[seg], full_bar(s), k0, n0);
           }
@@ -719,23 +742,23 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
     uint32_t tl = 0;
     const bool do_pf = p.epi.rms_p32 != nullptr && p.rms_prefetch != 0;
     if (do_pf && (int)blockIdx.x < num_tiles)
-      rms_prefetch_row(p.epi, (blockIdx.x % tiles_m) * BM + q * 32 + lane,
-                       (blockIdx.x / tiles_m) * BN + col_lo, COLS_PER_WARP);
+      rms_prefetch_row(p.epi, (N_FAST ? blockIdx.x / tiles_n : blockIdx.x % tiles_m) * BM + q * 32 + lane,
+                       (N_FAST ? blockIdx.x % tiles_n : blockIdx.x / tiles_m) * p.bn_eff + col_lo, COLS_PER_WARP);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * BN;
+      const int m0 = (N_FAST ? tile / tiles_n : tile % tiles_m) * BM;
+      const int n0 = (N_FAST ? tile % tiles_n : tile / tiles_m) * p.bn_eff;
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       if (do_pf && tile + (int)gridDim.x < num_tiles) {
         const int nxt = tile + gridDim.x;
-        rms_prefetch_row(p.epi, (nxt % tiles_m) * BM + q * 32 + lane,
-                         (nxt / tiles_m) * BN + col_lo, COLS_PER_WARP);
+        rms_prefetch_row(p.epi, (N_FAST ? nxt / tiles_n : nxt % tiles_m) * BM + q * 32 + lane,
+                         (N_FAST ? nxt % tiles_n : nxt / tiles_m) * p.bn_eff + col_lo, COLS_PER_WARP);
       }
       mbar_wait(tfull_bar(acc), aph, 14);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = col_lo; c < col_lo + COLS_PER_WARP; c += 32) {
-        if (n0 + c >= p.epi.N) break;  // warp-uniform
+        if (c >= p.bn_eff || n0 + c >= p.epi.N) break;  // warp-uniform
         uint32_t raw[32];
         tmem_ld32(t_row + (uint32_t)c, raw);
         tmem_ld_wait();
@@ -910,10 +933,10 @@ static constexpr size_t smem_bytes_persistent() {
          EPI_WARPS * 32 * EPI_LD * 4 + 1024;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS = 4>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS = 4, bool N_FAST = false>
 static int launch_persistent_cfg(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
-  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS>;
+  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST>;
   static bool attr_set = false;
   constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS>();
   if (!attr_set) {
@@ -975,65 +998,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     CC_REQUIRE(d->k[s] > 0, "cc_gemm: segment %d has k=%d", s, d->k[s]);
     p.kblocks[s] = (d->k[s] + BK - 1) / BK;
     total += p.kblocks[s];
-    int rc;
-    if (a_mn)  // stored [K, M]
-      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->M, (uint64_t)d->k[s], (uint64_t)d->lda[s], 64, BK);
-    else  // stored [M, K]
-      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->k[s], (uint64_t)d->M, (uint64_t)d->lda[s], BK, BM);
-    if (rc) return rc;
-    if (b_mn)  // stored [K, N]
-      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->N, (uint64_t)d->k[s], (uint64_t)d->ldb[s], 64, BK);
-    else  // stored [N, K]
-      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->k[s], (uint64_t)d->N, (uint64_t)d->ldb[s], BK, (uint32_t)bn);
-    if (rc) return rc;
   }
   p.total_kblocks = total;
-  p.rms_prefetch = env_int("CC_GEMM_RMS_PREFETCH", 1);
+  p.rms_prefetch = env_int("CC_GEMM_RMS_PREFETCH", 0);  // measured slower (profiles/)
 
-  // UMMA descriptors.  K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=16B),
-  // K advance = 32 B inside the swizzle row.  MN-major, 128B swizzle: 64-element MN atoms are
-  // separate TMA boxes 64*BK*2 = 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance =
-  // 16 rows * 128 B.
-  const uint32_t mn_lbo = (uint32_t)env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
-  const uint32_t mn_sbo = (uint32_t)env_int("CC_GEMM_MN_SBO", 1024);
-  const uint32_t mn_kstep = (uint32_t)env_int("CC_GEMM_MN_KSTEP", UMMA_K * 128);
-  const uint32_t k_lbo = (uint32_t)env_int("CC_GEMM_K_LBO", 16);
-  const uint32_t k_sbo = (uint32_t)env_int("CC_GEMM_K_SBO", 1024);
-  p.adesc_hi = a_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
-  p.bdesc_hi = b_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
-  p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
-  p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
-  // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
-  // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
-            ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-  EpiParams& e = p.epi;
-  e.M = d->M;
-  e.N = d->N;
-  e.alpha = d->alpha;
-  e.bias = d->bias;
-  e.act = d->act;
-  e.dact_y = (const bf16*)d->dact_y;
-  e.ld_dact = d->ld_dact;
-  e.dact = d->dact_y ? d->dact : 0;
-  e.out16 = (bf16*)d->out16;
-  e.ld16 = d->ld16;
-  e.beta16 = d->beta16;
-  e.out32 = d->out32;
-  e.ld32 = d->ld32;
-  e.beta32 = d->beta32;
-  e.rms_p32 = d->rms_p32;
-  e.rms_ms = d->rms_ms;
-  e.rms_mom = d->rms_mom;
-  e.rms_p16 = (bf16*)d->rms_p16;
-  e.rms_ld = d->rms_ld;
-  e.rms_lr = d->rms_lr;
-  e.rms_rho = d->rms_rho;
-  e.rms_momentum = d->rms_momentum;
-  e.rms_eps = d->rms_eps;
-
-  const int mt = (d->M + BM - 1) / BM, nt = (d->N + bn - 1) / bn;
+  const int mt = (d->M + BM - 1) / BM;
+  int nt = (d->N + bn - 1) / bn;
   // split-K when the tile grid cannot fill the machine and the reduction is long
   int splits = 1;
   const long long Mpad = (long long)mt * BM, Npad = (long long)nt * bn;
@@ -1067,14 +1037,109 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     p.kb_per_split = total;
     splits = 1;
   }
+  const bool persistent =
+      splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr);
 
-  if (splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr)) {
+  // effective tile width of the persistent kernel: the candidate (multiple of 32) that minimises
+  // waves x (width + fixed per-tile cost); e.g. N = 3369 at batch 2048 is 224 tiles of 256
+  // (1.51 waves on 148 SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each 25 % shorter)
+  int bn_eff = bn;
+  if (persistent && bn == 256 && d->rms_p32 == nullptr) {
+    const int forced = env_int("CC_GEMM_BN_EFF", 0);
+    if (forced >= 32 && forced <= 256 && forced % 32 == 0) {
+      bn_eff = forced;
+    } else {
+      long long best = -1;
+      for (int cand = 256; cand >= 128; cand -= 32) {
+        const long long tiles = (long long)mt * ((d->N + cand - 1) / cand);
+        const long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * (cand + 32);
+        if (best < 0 || cost < best) {
+          best = cost;
+          bn_eff = cand;
+        }
+      }
+    }
+    nt = (d->N + bn_eff - 1) / bn_eff;
+  }
+  p.bn_eff = bn_eff;
+  p.b_boxes = (bn_eff + 63) / 64;
+  p.stage_tx = (unsigned)(BM * BK * 2 + (b_mn ? p.b_boxes * 64 * BK * 2 : bn_eff * BK * 2));
+
+  for (int s = 0; s < d->nseg; ++s) {
+    int rc;
+    if (a_mn)  // stored [K, M]
+      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->M, (uint64_t)d->k[s], (uint64_t)d->lda[s], 64, BK);
+    else  // stored [M, K]
+      rc = make_map(&maps.a[s], d->a[s], (uint64_t)d->k[s], (uint64_t)d->M, (uint64_t)d->lda[s], BK, BM);
+    if (rc) return rc;
+    if (b_mn)  // stored [K, N]
+      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->N, (uint64_t)d->k[s], (uint64_t)d->ldb[s], 64, BK);
+    else  // stored [N, K]
+      rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->k[s], (uint64_t)d->N, (uint64_t)d->ldb[s], BK,
+                    (uint32_t)(persistent ? bn_eff : bn));
+    if (rc) return rc;
+  }
+
+  // UMMA descriptors.  K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=16B),
+  // K advance = 32 B inside the swizzle row.  MN-major, 128B swizzle: 64-element MN atoms are
+  // separate TMA boxes 64*BK*2 = 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance =
+  // 16 rows * 128 B.
+  const uint32_t mn_lbo = (uint32_t)env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
+  const uint32_t mn_sbo = (uint32_t)env_int("CC_GEMM_MN_SBO", 1024);
+  const uint32_t mn_kstep = (uint32_t)env_int("CC_GEMM_MN_KSTEP", UMMA_K * 128);
+  const uint32_t k_lbo = (uint32_t)env_int("CC_GEMM_K_LBO", 16);
+  const uint32_t k_sbo = (uint32_t)env_int("CC_GEMM_K_SBO", 1024);
+  p.adesc_hi = a_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
+  p.bdesc_hi = b_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
+  p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
+  p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
+  // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
+  // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
+            ((b_mn ? 1u : 0u) << 16) | ((uint32_t)((persistent ? bn_eff : bn) >> 3) << 17) |
+            ((uint32_t)(BM >> 4) << 24);
+
+  EpiParams& e = p.epi;
+  e.M = d->M;
+  e.N = d->N;
+  e.alpha = d->alpha;
+  e.bias = d->bias;
+  e.act = d->act;
+  e.dact_y = (const bf16*)d->dact_y;
+  e.ld_dact = d->ld_dact;
+  e.dact = d->dact_y ? d->dact : 0;
+  e.out16 = (bf16*)d->out16;
+  e.ld16 = d->ld16;
+  e.beta16 = d->beta16;
+  e.out32 = d->out32;
+  e.ld32 = d->ld32;
+  e.beta32 = d->beta32;
+  e.rms_p32 = d->rms_p32;
+  e.rms_ms = d->rms_ms;
+  e.rms_mom = d->rms_mom;
+  e.rms_p16 = (bf16*)d->rms_p16;
+  e.rms_ld = d->rms_ld;
+  e.rms_lr = d->rms_lr;
+  e.rms_rho = d->rms_rho;
+  e.rms_momentum = d->rms_momentum;
+  e.rms_eps = d->rms_eps;
+  e.rms_cs = env_int("CC_GEMM_RMS_CS", 1);
+
+  if (persistent) {
     // fused optimiser on weight gradients (both operands MN-major, no epilogue math): the
     // epilogue streams 26 B per element, so it gets 8 warps (twice the loads in flight) and
     // the main loop one stage less
     if (bn == 256 && d->rms_p32 != nullptr && a_mn && b_mn && d->alpha == 1.f &&
-        d->bias == nullptr && d->act == 0 && e.dact == 0 && env_int("CC_GEMM_RMS_WARPS", 8) == 8)
+        d->bias == nullptr && d->act == 0 && e.dact == 0 && env_int("CC_GEMM_RMS_WARPS", 8) == 8) {
+      // raster: walk along N (DRAM-page-local optimiser stream) when the whole B operand
+      // (dZ, batch x N) stays L2-resident across row blocks; otherwise keep m fastest so the
+      // CTAs of a wave share one B tile and A (X^T) is the L2-resident operand
+      int nfast = env_int("CC_GEMM_RMS_NFAST", -1);
+      if (nfast < 0) nfast = ((long long)total * BK * d->N * 2 <= (48ll << 20)) ? 1 : 0;
+      if (nfast != 0)
+        return launch_persistent_cfg<256, 3, true, true, false, 8, true>(maps, p, mt, nt, g_num_sms, st);
       return launch_persistent_cfg<256, 3, true, true, false, 8>(maps, p, mt, nt, g_num_sms, st);
+    }
     if (bn == 256) return launch_persistent<256, 4>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
     return launch_persistent<128, 6>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
   }

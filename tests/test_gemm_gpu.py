@@ -233,3 +233,51 @@ def test_wgrad_with_fused_rmsprop_epilogue(K, N, B):
                     rms=(p32b, None, msb, momb, lr, rho, mo, eps))
     torch.cuda.synchronize()
     assert torch.equal(p32b, p32) and torch.equal(msb, ms)
+
+
+@pytest.mark.parametrize("bn_eff", [128, 160, 192, 224, 256])
+@pytest.mark.parametrize("orient", ["fwd", "dgrad", "wgrad"])
+def test_effective_tile_width(bn_eff, orient, monkeypatch):
+    """Persistent kernel with a narrower effective tile (wave-quantisation heuristic of
+    gemm_sm100.cu): every candidate width, all three operand-major combinations, N not a
+    multiple of the width, bias + activation epilogue."""
+    ops = _ops()
+    monkeypatch.setenv("CC_GEMM_BN_EFF", str(bn_eff))
+    M, N, K = 300, 1000, 200
+    bias = torch.randn(N, device="cuda")
+    if orient == "fwd":
+        a, b = _rand(M, K, 21), _rand(K, N, 22)
+        ref, am, bm = a.float() @ b.float(), 0, 1
+    elif orient == "dgrad":
+        a, b = _rand(M, K, 23), _rand(N, K, 24)
+        ref, am, bm = a.float() @ b.float().t(), 0, 0
+    else:
+        a, b = _rand(K, M, 25), _rand(K, N, 26)
+        ref, am, bm = a.float().t() @ b.float(), 1, 1
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    out16 = ops.alloc2d(M, N)
+    out32 = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, [da], [db], [K], am, bm, bias=bias, act=ops.ACT_SIGMOID, out16=out16,
+             out32=out32, use_ws=False)
+    torch.cuda.synchronize()
+    ref = torch.sigmoid(ref + bias.cpu())
+    _check(out32, ref, K, False)
+    _check(out16, ref, K, True)
+
+
+def test_effective_tile_width_auto_matches_full_width(monkeypatch):
+    """The heuristic's pick (here 192 for N = 3369 at 16 row tiles) gives the same result as
+    the full 256-wide tile."""
+    ops = _ops()
+    M, N, K = 2048, 3369, 320
+    a, b = _rand(M, K, 31), _rand(K, N, 32)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    outs = []
+    for forced in ("0", "256"):
+        monkeypatch.setenv("CC_GEMM_BN_EFF", forced)
+        o = ops.alloc2d(M, N, dtype=torch.float32)
+        ops.gemm(M, N, [da], [db], [K], 0, 1, out32=o, use_ws=False)
+        torch.cuda.synchronize()
+        outs.append(o.cpu())
+    assert torch.equal(outs[0], outs[1])
+    _check(outs[0], a.float() @ b.float(), K, False)
