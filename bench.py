@@ -44,6 +44,16 @@ def peaks():
                 "source": "fallback (B200_PROFILING.md)"}
 
 
+def gemm_traffic():
+    """DRAM bytes per launch of the two GEMM sets, from the committed ncu pass over one step
+    (profiles/r01_gemm_traffic.json, written by tools/summarize_traffic.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 # ------------------------------------------------------------------------------ data
 def synth_csr(n_cells, n_genes, seed, device):
     """10x-shaped synthetic counts as a CSR: nnz/cell ~
@@ -355,19 +365,34 @@ def run_ours(args):
         torch.cuda.synchronize()
     finally:
         ops.gemm = real_gemm
-    gemm_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gemm_graph):
-        for a, k in calls:
-            real_gemm(*a, **k)
-    gemm_graph.replay()
-    torch.cuda.synchronize()
-    reps = 3
-    ev0.record()
-    for _ in range(reps):
-        gemm_graph.replay()
-    ev1.record()
-    torch.cuda.synchronize()
-    gemm_ms = [ev0.elapsed_time(ev1) / reps, len(calls)]
+    def time_calls(subset, reps=3):
+        """CUDA-event time of `subset` re-issued as one CUDA graph (ms per replay)."""
+        if not subset:
+            return 0.0
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for a, k in subset:
+                real_gemm(*a, **k)
+        gr.replay()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            gr.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+
+    # launches whose epilogue applies RMSprop stream 26 B per parameter: HBM-bound, reported
+    # against the HBM roofline; everything else is the tensor-bound set
+    # (N > 128 selects the 256-wide, 8-epilogue-warp instantiation; the few tiny fused wgrads
+    # stay in the first set, as in tools/summarize_traffic.py)
+    is_fused = lambda c: c[1].get("rms") is not None and c[0][1] > 128
+    fused_calls = [c for c in calls if is_fused(c)]
+    plain_calls = [c for c in calls if not is_fused(c)]
+    gemm_ms = [time_calls(calls), len(calls), time_calls(plain_calls), len(plain_calls),
+               time_calls(fused_calls), len(fused_calls),
+               sum(2.0 * a[0] * a[1] * a[4][0] for a, k in fused_calls),      # algorithmic FLOPs
+               sum(26.0 * a[0] * a[1] for a, k in fused_calls)]               # algorithmic bytes
     table_path = os.environ.get("CELLCOMM_BENCH_GEMM_TABLE")
     if table_path and rank == 0:
         # per-shape table: each distinct launch replayed alone as a small graph
@@ -405,10 +430,15 @@ def run_ours(args):
     step_ms = ms_resident / args.steps
     value = B * world * args.steps / (ms_resident / 1e3)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
-    gemm_total, gemm_launches = gemm_ms
+    (gemm_total, gemm_launches, plain_ms, plain_launches, fused_ms, fused_launches, fused_flops,
+     fused_bytes) = gemm_ms
     flops_step = FLOP_PER_CELL_TRAIN * B
-    achieved_tf = flops_step / (gemm_total / 1e3) / 1e12
+    # tensor-bound set: all Dense forward / dgrad GEMMs (+ the wgrads when the optimiser is not
+    # fused); its algorithmic FLOPs are the step's minus the fused wgrads' share
+    tensor_flops = flops_step - fused_flops
+    achieved_tf = tensor_flops / (plain_ms / 1e3) / 1e12
     peak_tf = pk["bf16_tflops_sustained"]
+    traffic = gemm_traffic()
     line = {
         "metric": "BiGAN train cells/sec", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
@@ -423,12 +453,20 @@ def run_ours(args):
                         "three loss floats read back per step"},
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Dense fwd/dgrad/wgrad)",
+            "bound": "tensor",
+            "kernel": "gemm_tcgen05_persistent_kernel (Dense fwd / dgrad GEMMs"
+                      + ("" if fused_launches else " / wgrad") + ")",
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf, "traffic": None,
+            "frac": achieved_tf / peak_tf,
+            "traffic": traffic.get("tensor_bytes_per_launch"),
+            "traffic_note": traffic.get("note"),
+            "algorithmic_per_launch": tensor_flops / max(plain_launches, 1),
+            "avg_launch_ms": plain_ms / max(plain_launches, 1),
             "peak_source": pk["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
             "frac_of_burst_peak": achieved_tf / pk["bf16_tflops"],
             "flops_per_step_algorithmic": flops_step,
+            "flops_per_step_in_these_launches": tensor_flops,
+            "ms_per_step": plain_ms, "launches_per_step": plain_launches,
             "gemm_ms_per_step": gemm_total, "gemm_launches_per_step": gemm_launches,
             "gemm_share_of_step": gemm_total / step_ms,
             "timing": "all GEMM launches of one step re-issued as a GEMM-only CUDA graph, "
@@ -436,6 +474,18 @@ def run_ours(args):
             "whole_step_tflops": flops_step / (step_ms / 1e3) / 1e12,
             "whole_step_frac": flops_step / (step_ms / 1e3) / 1e12 / peak_tf,
         },
+        "roofline_hbm": None if not fused_launches else {
+            "bound": "hbm",
+            "kernel": "gemm_tcgen05_persistent_kernel<..., 8 epilogue warps> (wgrad GEMM with Keras "
+                      "RMSprop applied in the epilogue)",
+            "achieved": fused_bytes / (fused_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": fused_bytes / (fused_ms / 1e3) / 1e9 / pk["hbm_gbs"],
+            "traffic": traffic.get("fused_bytes_per_launch"),
+            "algorithmic_per_launch": fused_bytes / fused_launches,
+            "avg_launch_ms": fused_ms / fused_launches,
+            "algorithmic_bytes_per_parameter": 26, "ms_per_step": fused_ms,
+            "launches_per_step": fused_launches, "flops_per_step_in_these_launches": fused_flops,
+            "peak_source": pk["source"] + ", HBM copy bandwidth"},
         "encode": {
             "metric": "encode cells/sec (E.predict over all cells)",
             "value": args.cells / (ms_enc / 1e3), "unit": "cells/s",
@@ -450,7 +500,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in oracle_step_rate(
-            args.ref_batch, 1, 0, args.genes, "first step, no warm-up").items()
+            args.ref_batch, 3, 1, args.genes, "1 warm-up + 3 timed steps").items()
             if k != "sec_per_step"}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -67,12 +67,13 @@ struct GemmParams {
   unsigned long long adesc_hi, bdesc_hi;
   unsigned int a_kstep, b_kstep;  // bytes to advance the start address per UMMA_K
   unsigned int idesc;
-  int rms_prefetch;  // fused optimiser: L2-prefetch the next tile's parameter / slot rows
   // persistent kernel: effective tile width (multiple of 32, <= BN).  The smem / TMEM layout
   // stays BN wide; a narrower MMA N trades a little per-tile efficiency for a tile count that
   // fills the last wave (N = 3369 at BN 256 is 1.51 waves, at 192 it is 1.95).
   int bn_eff;
   int b_boxes;            // MN-major B: 64-column TMA boxes per stage
+  int b_half_rows;        // K-major B in a 2-CTA cluster: rows of the tile each CTA loads
+  int cluster;            // 1 or 2 CTAs per cluster (persistent kernel)
   unsigned int stage_tx;  // bytes TMA delivers per stage
 };
 
@@ -158,6 +159,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One lane of a converged warp (elect.sync): ptxas then issues the uniform-datapath TMA / MMA
+// instructions under a plain predicate instead of a per-lane ELECT/BRA.U.ANY retry loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // --------------------------------------------------------------- epilogue math
@@ -494,7 +507,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u, 1);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_dst = smem_base + s * STAGE_BYTES;
         const uint32_t b_dst = a_dst + A_BYTES;
         const int k0 = kb_in_seg * BK;
@@ -529,7 +542,7 @@ gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(full_bar(s), ph, 2);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_src = smem_base + s * STAGE_BYTES;
         const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
@@ -585,32 +598,51 @@ gemm_tcgen05_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p) {
 
 // ------------------------------------------------------- persistent warp-specialised kernel
 // One CTA per SM loops over output tiles (m fastest, so concurrently running CTAs share the
-// same B / weight tile through L2).  192 threads: warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2-5 = epilogue.  The fp32 accumulator is double-buffered in TMEM (2 x BN columns), so
-// the epilogue of tile i overlaps the main loop of tile i+1, and the smem ring has STAGES
-// k-blocks in flight across tile boundaries.
-// Warm L2 with the NEXT tile's optimiser operands (fused RMSprop epilogue): one thread walks
-// the consecutive 128-byte lines of its row, so DRAM sees page-local bursts instead of the
-// scattered 128-byte demand reads of the chunked epilogue.
-__device__ __forceinline__ void rms_prefetch_row(const EpiParams& e, int r, int c_lo, int ncols) {
-  if (e.rms_p32 == nullptr || r >= e.M || c_lo >= e.N) return;
-  const long long off = (long long)r * e.rms_ld + c_lo;
-  const int n = min(ncols, e.N - c_lo);
-  for (int i = 0; i < n; i += 32) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_p32 + off + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_ms + off + i));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.rms_mom + off + i));
-  }
-}
-
+// same B / weight tile through L2).  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. =
+// epilogue.  The fp32 accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue
+// of tile i overlaps the main loop of tile i+1, and the smem ring has STAGES k-blocks in
+// flight across tile boundaries.
+//
+// CLUSTER = 2: two CTAs (an SM pair) work on vertically adjacent tiles (same n-tile, m-tiles
+// 2j and 2j+1).  Each CTA loads its own A tile and HALF of the shared B tile, multicast into
+// both CTAs' smem (cp.async.bulk.tensor ... .multicast::cluster), so the L2 -> SM operand
+// traffic per k-block drops from 48 KB to 32 KB per CTA -- the big GEMMs are bound by that
+// traffic (ncu: ~15.7 TB/s xbar reads at 74 % tensor-pipe activity), not by the tensor pipe.
+// A stage may only be refilled once BOTH CTAs' MMAs have consumed it: the empty barriers
+// count two arrivals and every tcgen05.commit is multicast to both CTAs.
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                               int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
 }
 
 // N_FAST: consecutive tiles walk along N (the contiguous direction of the output / parameter
 // matrix), so the CTAs of one wave cover whole output rows: used by the fused-optimiser wgrad,
 // whose epilogue streams 26 B per element and wants DRAM-page-local bursts.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false,
+          int CLUSTER = 1>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p,
                                const int tiles_m, const int tiles_n) {
@@ -619,6 +651,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
+  static_assert(CLUSTER == 1 || CLUSTER == 2, "cluster of 1 or 2 CTAs");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -631,19 +664,25 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 4));
-  // per-epilogue-warp 32x33 fp32 transpose tiles, after the barrier block
+  // per-epilogue-warp 32x36 fp32 transpose tiles, after the barrier block
   float* epi_stage = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 8u * (2 * STAGES + 6));  // 16-B aligned: 2*STAGES+6 is even
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m * tiles_n;
   const int nkb = p.total_kblocks;
+  // work units: one tile (CLUSTER 1) or a vertical pair of tiles (CLUSTER 2)
+  const int rank = (CLUSTER == 2) ? (int)cluster_ctarank() : 0;
+  const int tiles_mu = (tiles_m + CLUSTER - 1) / CLUSTER;
+  const int num_units = tiles_mu * tiles_n;
+  const int unit0 = (int)blockIdx.x / CLUSTER, unit_step = (int)gridDim.x / CLUSTER;
+  auto unit_m0 = [&](int u) { return ((N_FAST ? u / tiles_n : u % tiles_mu) * CLUSTER + rank) * BM; };
+  auto unit_n0 = [&](int u) { return (N_FAST ? u % tiles_n : u / tiles_mu) * p.bn_eff; };
 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CLUSTER);  // one commit from every CTA of the cluster
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -661,21 +700,21 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CLUSTER == 2) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (N_FAST ? tile / tiles_n : tile % tiles_m) * BM;
-      const int n0 = (N_FAST ? tile % tiles_n : tile / tiles_m) * p.bn_eff;
+    for (int u = unit0; u < num_units; u += unit_step) {
+      const int m0 = unit_m0(u), n0 = unit_n0(u);
       int seg = 0, kb_in_seg = 0;
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 11);
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb_in_seg * BK;
@@ -687,7 +726,19 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
           } else {
             tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
           }
-          if (B_MN) {
+          if (CLUSTER == 2) {
+            // this CTA's half of the B tile, delivered to both CTAs
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                if (j < p.b_boxes && (j & 1) == rank)
+                  tma_load_2d_mc(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j,
+                                 k0, (uint16_t)3);
+            } else {
+              tma_load_2d_mc(b_dst + rank * p.b_half_rows * (BK * 2), &maps.b[seg], full_bar(s), k0,
+                             n0 + rank * p.b_half_rows, (uint16_t)3);
+            }
+          } else if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               if (j < p.b_boxes)
@@ -706,7 +757,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t it = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int u = unit0; u < num_units; u += unit_step, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(tempty_bar(acc), aph ^ 1u, 12);  // epilogue has drained this accumulator
       tcgen05_fence_after();
@@ -716,7 +767,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
         const uint32_t ph = (it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph, 13);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_src = smem_base + s * STAGE_BYTES;
           const uint32_t b_src = a_src + A_BYTES;
 #pragma unroll
@@ -725,7 +776,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
             const uint64_t bdesc = p.bdesc_hi | (uint64_t)(((b_src + k * p.b_kstep) & 0x3FFFFu) >> 4);
             umma_bf16(d_tmem, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));
+          if (CLUSTER == 2) umma_commit_mc(empty_bar(s), (uint16_t)3);
+          else umma_commit(empty_bar(s));
           if (i == nkb - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
@@ -740,29 +792,21 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
     constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
     const int col_lo = (ew >> 2) * COLS_PER_WARP;
     uint32_t tl = 0;
-    const bool do_pf = p.epi.rms_p32 != nullptr && p.rms_prefetch != 0;
-    if (do_pf && (int)blockIdx.x < num_tiles)
-      rms_prefetch_row(p.epi, (N_FAST ? blockIdx.x / tiles_n : blockIdx.x % tiles_m) * BM + q * 32 + lane,
-                       (N_FAST ? blockIdx.x % tiles_n : blockIdx.x / tiles_m) * p.bn_eff + col_lo, COLS_PER_WARP);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (N_FAST ? tile / tiles_n : tile % tiles_m) * BM;
-      const int n0 = (N_FAST ? tile % tiles_n : tile / tiles_m) * p.bn_eff;
+    for (int u = unit0; u < num_units; u += unit_step, ++tl) {
+      const int m0 = unit_m0(u), n0 = unit_n0(u);
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      if (do_pf && tile + (int)gridDim.x < num_tiles) {
-        const int nxt = tile + gridDim.x;
-        rms_prefetch_row(p.epi, (N_FAST ? nxt / tiles_n : nxt % tiles_m) * BM + q * 32 + lane,
-                         (N_FAST ? nxt % tiles_n : nxt / tiles_m) * p.bn_eff + col_lo, COLS_PER_WARP);
-      }
       mbar_wait(tfull_bar(acc), aph, 14);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16) + acc * BN;
+      if (m0 < p.epi.M) {  // (the odd row tile of a pair may lie wholly below the matrix)
 #pragma unroll 1
-      for (int c = col_lo; c < col_lo + COLS_PER_WARP; c += 32) {
-        if (c >= p.bn_eff || n0 + c >= p.epi.N) break;  // warp-uniform
-        uint32_t raw[32];
-        tmem_ld32(t_row + (uint32_t)c, raw);
-        tmem_ld_wait();
-        epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
+        for (int c = col_lo; c < col_lo + COLS_PER_WARP; c += 32) {
+          if (c >= p.bn_eff || n0 + c >= p.epi.N) break;  // warp-uniform
+          uint32_t raw[32];
+          tmem_ld32(t_row + (uint32_t)c, raw);
+          tmem_ld_wait();
+          epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -771,6 +815,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmP
   }
   tcgen05_fence_before();
   __syncthreads();
+  // no CTA may leave while its peer can still multicast into its smem / arrive on its barriers
+  if (CLUSTER == 2) cluster_sync_all();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
                  "r"(TMEM_COLS)
@@ -933,21 +979,62 @@ static constexpr size_t smem_bytes_persistent() {
          EPI_WARPS * 32 * EPI_LD * 4 + 1024;
 }
 
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST, int CLUSTER>
+static int launch_persistent_one(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
+                                 int num_sms, cudaStream_t st) {
+  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, CLUSTER>;
+  static bool attr_set = false;
+  static int max_ctas = 0;
+  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS>();
+  constexpr int threads = 64 + 32 * EPI_WARPS;
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_ctas = num_sms;
+    if (CLUSTER > 1) {
+      // co-resident clusters (an SM pair each); the persistent loop strides by the grid size
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3((unsigned)(num_sms / CLUSTER * CLUSTER));
+      q.blockDim = dim3(threads);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CLUSTER;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int nclusters = 0;
+      CC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kern, &q));
+      CC_REQUIRE(nclusters >= 1, "cc_gemm: no %d-CTA cluster fits on this device", CLUSTER);
+      if (nclusters * CLUSTER < max_ctas) max_ctas = nclusters * CLUSTER;
+    }
+    attr_set = true;
+  }
+  const int units = ((mt + CLUSTER - 1) / CLUSTER) * nt;
+  int grid = units * CLUSTER < max_ctas ? units * CLUSTER : max_ctas / CLUSTER * CLUSTER;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p, mt, nt));
+  count_launch();
+  return 0;
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS = 4, bool N_FAST = false>
 static int launch_persistent_cfg(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
-  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST>;
-  static bool attr_set = false;
-  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS>();
-  if (!attr_set) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int tiles = mt * nt;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(maps, p, mt, nt);
-  CC_CHECK_LAUNCH();
-  return 0;
+  if (p.cluster == 2)
+    return launch_persistent_one<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, 2>(maps, p, mt, nt, num_sms, st);
+  return launch_persistent_one<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, 1>(maps, p, mt, nt, num_sms, st);
 }
 
 template <int BN, int STAGES, bool MATH>
@@ -1000,7 +1087,6 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     total += p.kblocks[s];
   }
   p.total_kblocks = total;
-  p.rms_prefetch = env_int("CC_GEMM_RMS_PREFETCH", 0);  // measured slower (profiles/)
 
   const int mt = (d->M + BM - 1) / BM;
   int nt = (d->N + bn - 1) / bn;
@@ -1040,9 +1126,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   const bool persistent =
       splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr);
 
-  // effective tile width of the persistent kernel: the candidate (multiple of 32) that minimises
-  // waves x (width + fixed per-tile cost); e.g. N = 3369 at batch 2048 is 224 tiles of 256
-  // (1.51 waves on 148 SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each 25 % shorter)
+  // 2-CTA clusters (B tile multicast) whenever there are at least two row tiles
+  p.cluster = (persistent && mt >= 2 && env_int("CC_GEMM_CLUSTER", 2) == 2 &&
+               (d->rms_p32 == nullptr || env_int("CC_GEMM_RMS_CLUSTER", 1) != 0)) ? 2 : 1;
+  // effective tile width of the persistent kernel: the candidate that minimises
+  // waves x (per-tile cost); e.g. N = 3369 at batch 2048 is 224 tiles of 256 (1.51 waves on 148
+  // SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each shorter).  The per-tile cost model is
+  // operand bytes (A is fixed, B scales with the width): the kernels are L2->SM bound.
   int bn_eff = bn;
   if (persistent && bn == 256 && d->rms_p32 == nullptr) {
     const int forced = env_int("CC_GEMM_BN_EFF", 0);
@@ -1050,9 +1140,10 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       bn_eff = forced;
     } else {
       long long best = -1;
-      for (int cand = 256; cand >= 128; cand -= 32) {
-        const long long tiles = (long long)mt * ((d->N + cand - 1) / cand);
-        const long long cost = ((tiles + g_num_sms - 1) / g_num_sms) * (cand + 32);
+      const int mu = (mt + p.cluster - 1) / p.cluster, slots = g_num_sms / p.cluster;
+      for (int cand = 256; cand >= 128; cand -= 64) {
+        const long long units = (long long)mu * ((d->N + cand - 1) / cand);
+        const long long cost = ((units + slots - 1) / slots) * (cand + 128);
         if (best < 0 || cost < best) {
           best = cost;
           bn_eff = cand;
@@ -1063,6 +1154,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   }
   p.bn_eff = bn_eff;
   p.b_boxes = (bn_eff + 63) / 64;
+  p.b_half_rows = bn_eff / 2;
   p.stage_tx = (unsigned)(BM * BK * 2 + (b_mn ? p.b_boxes * 64 * BK * 2 : bn_eff * BK * 2));
 
   for (int s = 0; s < d->nseg; ++s) {
@@ -1076,7 +1168,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->N, (uint64_t)d->k[s], (uint64_t)d->ldb[s], 64, BK);
     else  // stored [N, K]
       rc = make_map(&maps.b[s], d->b[s], (uint64_t)d->k[s], (uint64_t)d->N, (uint64_t)d->ldb[s], BK,
-                    (uint32_t)(persistent ? bn_eff : bn));
+                    (uint32_t)(persistent ? (p.cluster == 2 ? bn_eff / 2 : bn_eff) : bn));
     if (rc) return rc;
   }
 

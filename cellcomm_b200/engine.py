@@ -37,6 +37,9 @@ _SPLIT_PRECISION = None if _SPLIT_ENV == "auto" else int(_SPLIT_ENV)
 _SMALL_WIDTH = int(os.environ.get("CELLCOMM_B200_SMALL_WIDTH", "512"))
 # data parallel: reduce-scatter + sharded RMSprop + bf16 all-gather instead of all-reduce + full sweep
 _SHARD_OPTIMIZER = os.environ.get("CELLCOMM_B200_SHARD_OPT", "1") != "0"
+# ... in buckets of about this many parameters, each reduce-scattered on the side stream as soon
+# as the backward pass has produced its gradient (big layers are cut along their rows)
+_BUCKET_ELEMS = int(os.environ.get("CELLCOMM_B200_BUCKET_ELEMS", str(48 << 20)))
 
 
 # =========================================================================== graph specs
@@ -199,40 +202,58 @@ class _NoDist:
     def all_reduce(self, t):
         return t
 
+    all_reduce_grad = all_reduce
+
 
 class TorchDist:
     """Data-parallel plumbing over torch.distributed (NCCL over NVLink on the GPU box, gloo in
     the CPU tests): sum all-reduces of BN statistics, flat gradients and the loss buffer.
     Every rank holds the full weights and 1/world_size of each batch's rows."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, grad_group=None):
         import torch.distributed as dist
         self._dist, self.group = dist, group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # gradient reduce-scatter / weight all-gather run on a side stream while the backward
+        # pass keeps issuing small BatchNorm all-reduces on the main stream.  torch serialises
+        # the collectives of ONE process group on its NCCL stream, so the bulk traffic gets a
+        # communicator of its own (collective call: every rank constructs TorchDist).
+        self.grad_group = grad_group
+        if grad_group is None and self.world_size > 1 and group is None and \
+                dist.get_backend() == "nccl":
+            self.grad_group = dist.new_group(ranks=list(range(self.world_size)))
+        if self.grad_group is None:
+            self.grad_group = group
 
     def all_reduce(self, t):
         if self.world_size > 1:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_reduce_grad(self, t):
+        """Sum all-reduce on the gradient communicator (side-stream traffic)."""
+        if self.world_size > 1:
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.grad_group)
+        return t
+
     def reduce_scatter(self, out_shard, full):
         """out_shard = this rank's 1/world slice of sum_over_ranks(full)."""
         if self._dist.get_backend(self.group) == "nccl":
             self._dist.reduce_scatter_tensor(out_shard, full, op=self._dist.ReduceOp.SUM,
-                                             group=self.group)
+                                             group=self.grad_group)
         else:   # gloo (CPU tests) has no reduce-scatter: all-reduce and slice
-            self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.group)
+            self._dist.all_reduce(full, op=self._dist.ReduceOp.SUM, group=self.grad_group)
             n = out_shard.numel()
             out_shard.copy_(full[self.rank * n:(self.rank + 1) * n])
 
     def all_gather(self, full, shard):
         """full = concat over ranks of `shard` (shard may be the matching slice of full)."""
         if self._dist.get_backend(self.group) == "nccl":
-            self._dist.all_gather_into_tensor(full, shard, group=self.group)
+            self._dist.all_gather_into_tensor(full, shard, group=self.grad_group)
         else:
             parts = [torch.empty_like(shard) for _ in range(self.world_size)]
-            self._dist.all_gather(parts, shard.clone(), group=self.group)
+            self._dist.all_gather(parts, shard.clone(), group=self.grad_group)
             full.copy_(torch.cat(parts))
 
 
@@ -259,6 +280,7 @@ class Net:
         self.device = device
         self.dist = dist or _NoDist()
         self._alloc_params(generator)
+        self._build_buckets()
         self.act = {}      # forward activations (bf16; fp32 for tensors in self.hp)
         self.shadow = {}   # bf16 copies of fp32 activations that also feed a GEMM
         self.grad = {}     # activation gradients, always fp32
@@ -291,6 +313,9 @@ class Net:
             if lay[0] == "dense":
                 K, N = sum(lay[1]), lay[2]
                 ldn = ops.pad_ld(N)
+                # 4096-element alignment: any layer / 64-row boundary can delimit a gradient
+                # bucket whose 1/world shards (world <= 16) stay 256-element aligned
+                off = (off + 4095) // 4096 * 4096
                 meta.append({"kind": "dense", "K": K, "N": N, "ld": ldn, "w_off": off,
                              "act": lay[3], "in_widths": lay[1]})
                 off += K * ldn
@@ -341,6 +366,52 @@ class Net:
                 L["gamma"].fill_(1.0)
             self.layers.append(L)
         self.sync_compute_copy()
+
+    def _build_buckets(self):
+        """Gradient buckets of the data-parallel sharded update: contiguous ranges of the flat
+        kernel region [0, small_off).  A `piece` is the row range of one Dense kernel that one
+        wgrad GEMM writes (input segments of a Concatenate are separate GEMMs; segments of
+        more than two buckets' worth are cut at segment-relative multiples of 64 rows, which
+        keeps the X column slices TMA-aligned).  Consecutive pieces are grouped into buckets;
+        a bucket is reduce-scattered when its last piece has been issued."""
+        self.pieces, self.buckets = {}, []
+        dense = [(i, L) for i, L in enumerate(self.layers) if L["kind"] == "dense"]
+        flat = []
+        for n, (i, L) in enumerate(dense):
+            region_end = dense[n + 1][1]["w_off"] if n + 1 < len(dense) else self.small_off
+            ro, ld = 0, L["ld"]
+            segs = [k for k in L["in_widths"]]
+            for si, k in enumerate(segs):
+                if k == 0 or L["N"] == 0:
+                    ro += k
+                    continue
+                nchunk = max(1, round(k * ld / _BUCKET_ELEMS))
+                rows_per = max(64, ((k + nchunk - 1) // nchunk + 63) // 64 * 64) if nchunk > 1 else k
+                lo = 0
+                while lo < k:
+                    hi = min(k, lo + rows_per)
+                    last_of_layer = (si == len(segs) - 1 or not any(segs[si + 1:])) and hi == k
+                    piece = {"layer": i, "seg": si, "lo": ro + lo, "hi": ro + hi,
+                             "start": L["w_off"] + (ro + lo) * ld,
+                             "end": region_end if last_of_layer else L["w_off"] + (ro + hi) * ld}
+                    flat.append(piece)
+                    self.pieces.setdefault((i, si), []).append(piece)
+                    lo = hi
+                ro += k
+        cur = None
+        for pc in flat:
+            size = pc["end"] - pc["start"]
+            if cur is None or cur["end"] != pc["start"] or \
+                    (cur["end"] - cur["start"]) + size > _BUCKET_ELEMS * 5 // 4:
+                cur = {"start": pc["start"], "end": pc["end"], "pieces": 0, "pending": 0,
+                       "launched": False}
+                self.buckets.append(cur)
+            cur["end"] = pc["end"]
+            cur["pieces"] += 1
+            pc["bucket"] = cur
+        # gaps (alignment padding before a region, zero-width layers) carry zero gradients and
+        # zero weights: they can stay out of the collectives
+        self._bucket_scratch = None
 
     def sync_compute_copy(self):
         """bf16 compute copy <- fp32 master (after init / set_weights)."""
@@ -655,6 +726,9 @@ class Net:
         g, rows, A = self.g, c["rows"], c["A"]
         needs = self._needs(train, want)
         state = [False] * len(g.widths)
+        if train and self._bucketed():
+            for bk in self.buckets:
+                bk["pending"], bk["launched"] = bk["pieces"], False
         out_t = g.output
         seed = self._buf(self.grad, out_t)[:rows]
         if g.widths[out_t] > 0 and dout.data_ptr() != seed.data_ptr():
@@ -686,7 +760,7 @@ class Net:
                     ops.act_bwd(dy, A[out], dz, act)
                     dzs = [dz]
                 ro = 0
-                for i in node["ins"]:
+                for seg_index, i in enumerate(node["ins"]):
                     k = g.widths[i]
                     if k > 0:
                         # input gradient first: it must see this layer's weights BEFORE the
@@ -707,9 +781,19 @@ class Net:
                                 sl = slice(ro, ro + k)
                                 rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
                                        LR, RHO, MOMENTUM, EPSILON)
-                            dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
-                            ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs], dw,
-                                            rms=rms)
+                            if self._bucketed():
+                                # data parallel: one GEMM per gradient piece, and the piece's
+                                # bucket goes to the side stream as soon as it is complete
+                                for pc in self.pieces.get((node["layer"], seg_index), ()):
+                                    a, b = pc["lo"] - ro, pc["hi"] - ro
+                                    ops.dense_wgrad([p_[0][:, a:b] for p_ in pairs],
+                                                    [p_[1] for p_ in pairs],
+                                                    L["dw"][pc["lo"]:pc["hi"]])
+                                    self._piece_done(pc)
+                            else:
+                                dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
+                                ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs],
+                                                dw, rms=rms)
                     ro += k
                 if train:
                     if out in self.prebn:
@@ -794,6 +878,46 @@ class Net:
             self._opt_event = torch.cuda.Event()
             self._opt_event.record(self.opt_stream)
 
+    def _bucketed(self):
+        """Data-parallel sharded update in per-bucket collectives (world a power of two <= 16:
+        every bucket is a multiple of 64 elements, so 1/world shards stay 16-byte aligned)."""
+        W = self.dist.world_size
+        return (W > 1 and _SHARD_OPTIMIZER and not self.fuse_optimizer and 64 % W == 0
+                and len(self.buckets) > 0)
+
+    def _piece_done(self, pc):
+        bk = pc["bucket"]
+        bk["pending"] -= 1
+        if bk["pending"] == 0:
+            self._launch_bucket(bk)
+
+    def _launch_bucket(self, bk):
+        """reduce-scatter -> RMSprop on this rank's shard -> all-gather of the bf16 weights, for
+        one bucket, on the optimiser stream (ordered after the gradient's wgrad GEMMs)."""
+        if bk["launched"]:
+            return
+        bk["launched"] = True
+        W, r = self.dist.world_size, self.dist.rank
+        n = (bk["end"] - bk["start"]) // W
+        sl = slice(bk["start"] + r * n, bk["start"] + (r + 1) * n)
+        if self._bucket_scratch is None:
+            biggest = max(b["end"] - b["start"] for b in self.buckets) // W
+            self._bucket_scratch = torch.empty(biggest, dtype=torch.float32, device=self.device)
+        shard = self._bucket_scratch[:n]
+
+        def run():
+            self.dist.reduce_scatter(shard, self.g32[bk["start"]:bk["end"]])
+            ops.rmsprop_step(self.p32[sl], self.p16[sl], shard, self.ms[sl], self.mom[sl], LR, RHO,
+                             MOMENTUM, EPSILON)
+            self.dist.all_gather(self.p16[bk["start"]:bk["end"]], self.p16[sl])
+
+        if self.opt_stream is None:
+            run()
+            return
+        self.opt_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.opt_stream):
+            run()
+
     def _reduce_and_update(self):
         """Data-parallel update.  world == 1: one sweep.  world > 1 (ZeRO-1 style): reduce-scatter
         the fp32 gradient, RMSprop on this rank's 1/world shard of the flat buffers (1/world of
@@ -801,6 +925,17 @@ class Net:
         master copy is then only current on its owner shard; gather_master() refreshes it."""
         W = self.dist.world_size
         K = self.small_off                      # Dense kernels: [0, K); biases + BN: [K, n_flat)
+        if self._bucketed():
+            # most buckets were launched from backward(); flush the rest (layers the backward
+            # pass did not reach), then the replicated update of biases and BN gamma/beta
+            for bk in self.buckets:
+                self._launch_bucket(bk)
+            tail = slice(K, self.n_flat)
+            self.dist.all_reduce_grad(self.g32[tail])
+            ops.rmsprop_step(self.p32[tail], self.p16[tail], self.g32[tail], self.ms[tail],
+                             self.mom[tail], LR, RHO, MOMENTUM, EPSILON)
+            self._master_stale = True
+            return
         if W == 1 or not _SHARD_OPTIMIZER or K == 0 or K % (W * 256) != 0:
             self.dist.all_reduce(self.g32)
             ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
@@ -824,10 +959,14 @@ class Net:
     def gather_master(self):
         """Make the fp32 master weights current on every rank (sharded-optimiser runs)."""
         if self._master_stale and self.dist.world_size > 1:
-            W = self.dist.world_size
-            n = self.small_off // W
-            sl = slice(self.dist.rank * n, (self.dist.rank + 1) * n)
-            self.dist.all_gather(self.p32[:self.small_off], self.p32[sl].clone())
+            W, r = self.dist.world_size, self.dist.rank
+            if self._bucketed():
+                ranges = [(b["start"], b["end"]) for b in self.buckets]
+            else:
+                ranges = [(0, self.small_off)]
+            for a, b in ranges:
+                n = (b - a) // W
+                self.dist.all_gather(self.p32[a:b], self.p32[a + r * n:a + (r + 1) * n].clone())
         self._master_stale = False
 
     def _wait_optimizer(self):
@@ -982,12 +1121,13 @@ class BiGanEngine:
         self._graphs = {}
         for n in self.nets.values():
             n.on_grow = self._graphs.clear
-        # default: flat RMSprop sweeps on a side stream, overlapped with the next network's
-        # forward (measured faster than the fused wgrad epilogue, which streams the optimiser
-        # state at ~3.5 TB/s against the sweep's 5.5-5.8 TB/s); CELLCOMM_B200_FUSE_OPT=1 selects
-        # the fused epilogue (single GPU only)
-        self.set_fused_optimizer(self.dist.world_size == 1 and
-                                 os.environ.get("CELLCOMM_B200_FUSE_OPT", "0") == "1")
+        # single GPU: Keras RMSprop is applied inside the wgrad GEMM epilogues (the accumulator IS
+        # the gradient: 26 B/parameter of optimiser traffic instead of a 4 B gradient write plus a
+        # 30 B/parameter sweep; -2.9 ms per 2048-cell step, profiles/README.md).  Data parallel
+        # runs must reduce the gradient first and use the sharded flat sweep instead.
+        # CELLCOMM_B200_FUSE_OPT=0 selects the flat sweep on one GPU too.
+        self.set_fused_optimizer(self.dist.world_size == 1 and self.device.type == "cuda" and
+                                 os.environ.get("CELLCOMM_B200_FUSE_OPT", "1") == "1")
         if self.device.type == "cuda" and os.environ.get("CELLCOMM_B200_ASYNC_OPT", "1") != "0":
             side = torch.cuda.Stream(device=self.device)
             for n in self.nets.values():

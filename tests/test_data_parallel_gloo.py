@@ -15,10 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, variant, Z, G, B, out):
+def _worker(rank, world, port, variant, Z, G, B, out, bucket_elems=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if bucket_elems:     # read when cellcomm_b200.engine is imported
+        os.environ["CELLCOMM_B200_BUCKET_ELEMS"] = str(bucket_elems)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import ops_emulator
     from cellcomm_b200 import engine as eng
@@ -29,6 +31,8 @@ def _worker(rank, world, port, variant, Z, G, B, out):
     orc = O.OracleBiGan(variant, Z, G, seed=0, dtype=torch.float64)
     e = eng.BiGanEngine(variant, Z, G, max_batch=B // world, device="cpu", seed=0,
                         dist=eng.TorchDist())
+    if bucket_elems:     # the big layers must really be cut into several row pieces / buckets
+        assert max(len(v) for v in e.D.pieces.values()) >= 2 and len(e.D.buckets) >= 3
     for n in ("G", "E", "D"):
         e.nets[n].set_weights([w.numpy() for w in orc.get_weights(n)])
     x, z, r = P._inputs(variant, Z, G, B, 11)
@@ -62,6 +66,17 @@ def test_two_ranks_equal_one_global_batch(tmp_path, variant, Z, G, B):
     out = str(tmp_path / "res.pt")
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, variant, Z, G, B, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["ok"], res
+    assert res["worst_weight_err"] <= 2e-4, res
+
+
+def test_two_ranks_bucketed_row_chunks(tmp_path):
+    """Same check with tiny gradient buckets: big kernels are cut along their rows, every
+    bucket is reduce-scattered / updated / all-gathered on its own."""
+    out = str(tmp_path / "res.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, "cont", 3, 150, 12, out, 2048), nprocs=2, join=True)
     res = torch.load(out)
     assert res["ok"], res
     assert res["worst_weight_err"] <= 2e-4, res
