@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 GENES, CELLS, Z = 33694, 30000, 3
 FLOP_PER_CELL_TRAIN = 13.237e9      # SURVEY.md App. B (dense-equivalent 2*M*N*K, Continuous)
 FLOP_PER_CELL_ENCODE = 0.3524e9
+FLOP_PER_CELL_TRAIN_CLASSIFY = 8.057e9     # ClassifyCellBiGan (BASELINE.json configs[3])
+FLOP_PER_CELL_ENCODE_CLASSIFY = 0.0684e9
+Z_CLASSIFY = 10                     # synthetic cell types
 
 
 def peaks():
@@ -153,19 +156,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def oracle_step_rate(batch, steps, warmup, genes, note):
+def oracle_step_rate(batch, steps, warmup, genes, note, variant="cont"):
     """cells/s of the oracle's trainings_step on the host cores (all threads)."""
     import torch
     from oracle import bigan_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    m = O.OracleBiGan("cont", Z, genes, seed=0)
+    Z = Z_CLASSIFY if variant == "classify" else 3
+    m = O.OracleBiGan(variant, Z, genes, seed=0)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(batch, genes, generator=g) < 0.06).float() * \
         (torch.poisson(torch.full((batch, genes), 1.2), generator=g) + 1)
-    masks = O.make_masks("cont", Z, genes, batch, 1)
+    masks = O.make_masks(variant, Z, genes, batch, 1)
     times = []
     for i in range(warmup + steps):
         z, r = torch.rand(batch, Z, generator=g), torch.rand(batch, Z, generator=g)
+        if variant == "classify":
+            z = torch.nn.functional.one_hot(torch.randint(0, Z, (batch,), generator=g), Z).float()
         t0 = time.perf_counter()
         m.trainings_step(x, z, r, masks)
         if i >= warmup:
@@ -187,8 +193,11 @@ def run_reference(args):
     if rank != 0:
         return
     batch = args.ref_batch
+    if args.workload == "encode":
+        return run_reference_encode(args)
     res = oracle_step_rate(batch, max(1, args.steps), max(0, args.warmup), args.genes,
-                           "same synthetic count model as the GPU arm")
+                           "same synthetic count model as the GPU arm",
+                           "classify" if args.workload == "classify" else "cont")
     line = {
         "impl": "reference", "metric": "BiGAN train cells/sec", "value": res["value"],
         "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -203,9 +212,13 @@ def run_reference(args):
 
 
 def workload_config(args, batch):
-    return {"workload": f"ContinuousCellBiGan trainings_step on synthetic 10x-shaped matrix "
-                        f"{args.cells} cells x {args.genes} genes (BASELINE.json configs[1])",
-            "cells": args.cells, "genes": args.genes, "encoding_size": Z,
+    classify = args.workload == "classify"
+    return {"workload": (f"ClassifyCellBiGan trainings_step, {Z_CLASSIFY} synthetic cell types, "
+                         if classify else "ContinuousCellBiGan trainings_step ") +
+                        f"on synthetic 10x-shaped matrix {args.cells} cells x {args.genes} genes "
+                        f"(BASELINE.json configs[{3 if classify else 1}])",
+            "cells": args.cells, "genes": args.genes,
+            "encoding_size": Z_CLASSIFY if classify else Z,
             "batch_per_gpu": batch, "l2_policy": "inputs larger than L2 (0.9-1.8 GB of bf16 "
             "weights streamed per update; every weight is rewritten between uses)"}
 
@@ -243,7 +256,16 @@ def run_ours(args):
     data = make_matrix(args.cells, args.genes, 20260101, dev)
     assert data.shape == (args.cells, args.genes)
     np.random.seed(1000 + rank)          # each rank samples its own cells (weak scaling)
-    trainer = CellTraining(data, batch_size=B, encoding_size=Z)
+    classify = args.workload == "classify"
+    Z = Z_CLASSIFY if classify else 3
+    if classify:
+        from cellcomm_b200.bigan_classify import ClassifyCellBiGan
+        trainer = CellTraining.__new__(CellTraining)     # the reference's trainer builds the
+        trainer.batch_size, trainer.data = B, data         # Continuous variant only
+        trainer.batches_per_iteration = 10
+        trainer.network = ClassifyCellBiGan(Z, gene_size=args.genes)
+    else:
+        trainer = CellTraining(data, batch_size=B, encoding_size=Z)
     net = trainer.network
     e = net._engine
     rowptr, colidx, values = data.device_csr(dev)
@@ -258,16 +280,35 @@ def run_ours(args):
 
     graphed = None
     if args.graph and world == 1:
-        graphed = e.capture_step((rowptr, colidx, values), args.genes, B, latents="device")
+        graphed = e.capture_step((rowptr, colidx, values), args.genes, B,
+                                 latents="host" if classify else "device")
+    # classify prior: one-hot of a uniform category (src/bigan_classify.py:117-119), resident pool
+    z_pool = None
+    if classify:
+        gz = torch.Generator(device=dev).manual_seed(7 + rank)
+        z_pool = torch.nn.functional.one_hot(
+            torch.randint(0, Z, (n_pre, B), generator=gz, device=dev), Z).float()
+        r_pool = torch.rand((n_pre, B, Z), generator=gz, device=dev)
+
+    def stage_latents(i):
+        if classify:
+            e.z32[:B].copy_(z_pool[i % n_pre], non_blocking=True)
+            e.r32[:B].copy_(r_pool[i % n_pre], non_blocking=True)
 
     def eager_step(i):
         ops.gather_rows(rowptr, colidx, values, args.genes, row_idx=idx_all[i], out16=x16)
-        e.draw_latents(B)
+        if classify:
+            stage_latents(i)
+            ops.cast_f32_to_bf16(e.z32[:B], e.z16[:B])
+            ops.cast_f32_to_bf16(e.r32[:B], e.r16[:B])
+        else:
+            e.draw_latents(B)
         return e.train_step(x16)
 
     def resident_step(i):
         if graphed is not None:
             graphed.idx.copy_(idx_all[i], non_blocking=True)
+            stage_latents(i)
             return graphed.replay()
         return eager_step(i)
 
@@ -304,6 +345,19 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
     clock_info = clocks.stop() if rank == 0 else None
+
+    if args.no_roofline:          # quick sweeps: the two train numbers only
+        if rank == 0:
+            print(json.dumps({
+                "metric": "BiGAN train cells/sec", "unit": "cells/s", "n_gpus": world,
+                "value": B * world * args.steps / (ms_resident / 1e3),
+                "ms_per_step": ms_resident / args.steps, "steps": args.steps,
+                "warmup": args.warmup, "clocks": clock_info,
+                "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "cells/s"},
+                "config": workload_config(args, B), "partial": "--no-roofline"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- encode-all-cells pass (E.predict over the whole matrix; each rank a row shard)
     shard = (args.cells + world - 1) // world
@@ -432,7 +486,8 @@ def run_ours(args):
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
     (gemm_total, gemm_launches, plain_ms, plain_launches, fused_ms, fused_launches, fused_flops,
      fused_bytes) = gemm_ms
-    flops_step = FLOP_PER_CELL_TRAIN * B
+    flops_step = (FLOP_PER_CELL_TRAIN_CLASSIFY if classify else FLOP_PER_CELL_TRAIN) * B
+    flop_encode = FLOP_PER_CELL_ENCODE_CLASSIFY if classify else FLOP_PER_CELL_ENCODE
     # tensor-bound set: all Dense forward / dgrad GEMMs (+ the wgrads when the optimiser is not
     # fused); its algorithmic FLOPs are the step's minus the fused wgrads' share
     tensor_flops = flops_step - fused_flops
@@ -490,7 +545,7 @@ def run_ours(args):
             "metric": "encode cells/sec (E.predict over all cells)",
             "value": args.cells / (ms_enc / 1e3), "unit": "cells/s",
             "e2e": args.cells / (ms_enc_e2e / 1e3), "cells": args.cells,
-            "tensor_frac": args.cells * FLOP_PER_CELL_ENCODE / (ms_enc / 1e3) / 1e12 /
+            "tensor_frac": args.cells * flop_encode / (ms_enc / 1e3) / 1e12 /
             (peak_tf * world), "d2h_bytes": args.cells * Z * 4,
         },
         "losses_last_step": last_losses, "setup_seconds": setup_s,
@@ -500,11 +555,164 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in oracle_step_rate(
-            args.ref_batch, 3, 1, args.genes, "1 warm-up + 3 timed steps").items()
+            args.ref_batch, 3, 1, args.genes, "1 warm-up + 3 timed steps",
+            "classify" if classify else "cont").items()
             if k != "sec_per_step"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ encode-only
+def run_encode(args):
+    """BASELINE.json configs[4]: encode-only pass (E.predict, src/bigan_basic.py:29-30, the
+    DbRecorder's call src/intercepts/db_recorder.py:85) over --encode-cells synthetic cells x
+    33,694 genes, rows sharded contiguously over the GPUs, no communication.  A step = one pass
+    over this rank's shard.  The 10x-shaped CSR is the 30k-cell synthetic matrix repeated."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cellcomm_b200 import ops
+    from cellcomm_b200.bigan_cont import ContinuousCellBiGan
+    from cellcomm_b200.cell_type_training import CellMatrix
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total = args.encode_cells
+    shard = (total + world - 1) // world
+    n_local = max(0, min(total, (rank + 1) * shard) - rank * shard)
+    base_cells = min(args.cells, n_local)
+    rp, ci, va = synth_csr(base_cells, args.genes, 20260102, dev)
+    reps = (n_local + base_cells - 1) // base_cells
+    nnz = int(rp[-1])
+    rowptr = np.concatenate([rp[:-1] + k * nnz for k in range(reps)] + [[reps * nnz]])
+    rowptr = rowptr[:n_local + 1].astype(np.int64)
+    colidx = np.tile(ci, reps)[:rowptr[-1]]
+    values = np.tile(va, reps)[:rowptr[-1]]
+    data = CellMatrix(rowptr, colidx, values, np.arange(1, n_local + 1), np.arange(1, args.genes + 1))
+    net = ContinuousCellBiGan(Z, gene_size=args.genes)
+    e = net._engine
+    d_rowptr, d_colidx, d_values = data.device_csr(dev)
+    tile_rows = args.encode_tile
+    tile = ops.alloc2d(tile_rows, args.genes, device=dev)
+    out = torch.empty((n_local, Z), dtype=torch.float32, device=dev)
+    e.reserve(tile_rows)
+
+    def one_pass():
+        for s_ in range(0, n_local, tile_rows):
+            m = min(tile_rows, n_local - s_)
+            ops.gather_rows(d_rowptr, d_colidx, d_values, args.genes, row_start=s_, n_rows=m,
+                            out16=tile[:m])
+            e.encode(tile[:m], out32=out[s_:s_ + m])
+
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    one_pass()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warm - 1):
+        one_pass()
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        one_pass()
+    ev1.record()
+    barrier()
+    launches = (ops.launch_count() - l0) * steps // (steps + warm - 1)
+    ms = ev0.elapsed_time(ev1)
+    # end to end: the public call, float32 host array back (12 B per cell D2H)
+    net.encoding_prediction(data)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        host = net.encoding_prediction(data)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    clock_info = clocks.stop() if rank == 0 else None
+    assert host.shape == (n_local, Z) and np.isfinite(host).all()
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        pk = peaks()
+        value = total * steps / (ms / 1e3)
+        tf = value * FLOP_PER_CELL_ENCODE / 1e12 / world
+        line = {
+            "metric": "encode cells/sec", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"encode-only pass, {total} synthetic cells x {args.genes} genes, "
+                                   f"ContinuousCellBiGan encoder (BASELINE.json configs[4])",
+                       "cells": total, "genes": args.genes, "encoding_size": Z,
+                       "tile_rows": tile_rows, "nnz_per_rank": int(rowptr[-1]),
+                       "l2_policy": "inputs larger than L2 (CSR shard %.1f GB, bf16 tiles 276 MB, "
+                                    "227 MB of encoder weights per tile)" % (rowptr[-1] * 8 / 1e9)},
+            "clocks": clock_info,
+            "e2e": {"value": total * steps / (ms_e2e / 1e3), "unit": "cells/s",
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n_local * Z * 4,
+                    "path": "network.encoding_prediction(CellMatrix): device-resident CSR -> "
+                            "float32 host array (the DbRecorder's call)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_persistent_kernel (encoder "
+                         "forward GEMMs)", "achieved": tf, "peak": pk["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
+                         "traffic": None, "note": "whole-pass rate (gather + 5 GEMMs + BN); "
+                         "0.3524 GFLOP per cell (SURVEY.md App. B)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = oracle_encode_rate(args.genes)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def oracle_encode_rate(genes, cells=2048):
+    """Oracle E.predict on the host cores: the reference's Keras predict batches 32 rows
+    (SURVEY.md A.7); rows are independent in inference, so the port runs 256-row tiles."""
+    import torch
+    from oracle import bigan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = O.OracleBiGan("cont", Z, genes, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(cells, genes, generator=g) < 0.06).float() * \
+        (torch.poisson(torch.full((cells, genes), 1.2), generator=g) + 1)
+    m.encoding_prediction(x[:256])
+    t0 = time.perf_counter()
+    for s_ in range(0, cells, 256):
+        m.encoding_prediction(x[s_:s_ + 256])
+    dt = time.perf_counter() - t0
+    return {"value": cells / dt, "unit": "cells/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{cells} cells x {genes} genes through the oracle's "
+            f"encoding_prediction in 256-row tiles (torch-CPU fp32 restatement of E.predict)"}
+
+
+def run_reference_encode(args):
+    res = oracle_encode_rate(args.genes, cells=4096)
+    print(json.dumps({
+        "impl": "reference", "metric": "encode cells/sec", "value": res["value"],
+        "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "encode-only pass (bounded sample)",
+                                        "genes": args.genes},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}}), flush=True)
 
 
 def main():
@@ -522,13 +730,22 @@ def main():
     ap.add_argument("--genes", type=int, default=GENES)
     ap.add_argument("--encode-tile", type=int, default=4096)
     ap.add_argument("--encode-reps", type=int, default=2)
+    ap.add_argument("--workload", default="train", choices=["train", "classify", "encode"],
+                    help="train: ContinuousCellBiGan trainings_step (BASELINE configs[1], the "
+                         "headline); classify: ClassifyCellBiGan (configs[3]); encode: the "
+                         "encode-only pass over --encode-cells cells (configs[4])")
+    ap.add_argument("--encode-cells", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true",
+                    help="train numbers only (tuning sweeps); the driver's runs never pass this")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("CELLCOMM_BENCH_GRAPH", "1")),
                     help="1: run the device-resident loop as one CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "encode":
+        run_encode(args)
     else:
         run_ours(args)
 

@@ -31,6 +31,21 @@ class GemmDesc(C.Structure):
         ("force_splits", c_i32), ("force_bn", c_i32),
         ("rms_p32", vp), ("rms_ms", vp), ("rms_mom", vp), ("rms_p16", vp), ("rms_ld", c_i64),
         ("rms_lr", c_f32), ("rms_rho", c_f32), ("rms_momentum", c_f32), ("rms_eps", c_f32),
+        ("route_world", c_i32), ("route_shard", c_i64), ("route_off0", c_i64),
+        ("route_base", vp * 16),
+    ]
+
+
+class PeerRmspropDesc(C.Structure):
+    """cc_peer_rmsprop_desc"""
+    _fields_ = [
+        ("world", c_i32), ("rank", c_i32),
+        ("grad", vp * 16), ("p16", vp * 16),
+        ("p32", vp), ("ms", vp), ("mom", vp),
+        ("start", c_i64), ("count", c_i64),
+        ("broadcast", c_i32),
+        ("lr", c_f32), ("rho", c_f32), ("momentum", c_f32), ("eps", c_f32),
+        ("ready", vp), ("epoch", c_u32),
     ]
 
 
@@ -92,6 +107,9 @@ SIGNATURES = {
                                   c_f32, c_f32, vp]),
     "cc_bias_act": (C.c_int, [vp, c_i32, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
     "cc_fill_f32": (C.c_int, [vp, c_f32, c_i64, vp]),
+    "cc_peer_rmsprop": (C.c_int, [C.POINTER(PeerRmspropDesc), vp]),
+    "cc_peer_signal": (C.c_int, [C.POINTER(vp), c_i32, c_u32, vp]),
+    "cc_peer_wait": (C.c_int, [vp, c_i32, c_u32, vp]),
 }
 
 

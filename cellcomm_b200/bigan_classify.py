@@ -134,6 +134,15 @@ class ClassifyCellBiGan(BasicBiGan):
         g_loss, e_loss, d_loss = eng.train_step(x16)
         return g_loss, e_loss, d_loss
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, path):
+        """Weights, RMSprop slots, BN moving statistics and RNG position -> one .npz (the
+        reference has no checkpointing)."""
+        self._require_engine().save_checkpoint(path)
+
+    def load_checkpoint(self, path):
+        self._require_engine().load_checkpoint(path)
+
     # ------------------------------------------------------------------ plumbing
     def _require_engine(self):
         if self._engine is None:

@@ -52,6 +52,12 @@ struct EpiParams {
   long long rms_ld;
   float rms_lr, rms_rho, rms_momentum, rms_eps;
   int rms_cs;  // evict-first (ld/st.global.cs) hints on the optimiser state stream
+  // routed fp32 output (data-parallel wgrad): element `rel` of the bucket goes to the rank that
+  // owns it, route_base[owner] + rel (peer-mapped staging slot; own share: local memory)
+  int route_world;
+  unsigned int route_shard;
+  long long route_off0;
+  float* route_base[CC_PEER_MAX];
 };
 
 struct GemmParams {
@@ -403,7 +409,29 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
       });
     }
   }
-  if (e.out32 != nullptr) {
+  if (e.route_world > 0) {
+    // the reduce-scatter's data movement, done by the GEMM: store each row segment to its owner
+    const long long rel0 = e.route_off0 + (long long)rbase * e.ld32 + c;
+    const long long step = 4 * e.ld32;
+    const unsigned last = (unsigned)e.route_world - 1u;
+    const bool vec = ncol == 4 && (e.ld32 & 3) == 0 && ((c & 3) == 0);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < nrow) {
+        const long long rel = rel0 + t * step;
+        const unsigned owner = min((unsigned)((unsigned long long)rel / e.route_shard), last);
+        float* dst = e.route_base[owner] + rel;
+        if (vec) {
+          *reinterpret_cast<float4*>(dst) = g[t];
+        } else {
+          dst[0] = g[t].x;
+          if (ncol > 1) dst[1] = g[t].y;
+          if (ncol > 2) dst[2] = g[t].z;
+          if (ncol > 3) dst[3] = g[t].w;
+        }
+      }
+    }
+  } else if (e.out32 != nullptr) {
     float* o = e.out32 + (long long)rbase * e.ld32 + c;
     const long long step = 4 * e.ld32;
     if (ncol == 4 && !e.beta32 && (e.ld32 & 3) == 0 && ((c & 3) == 0) &&
@@ -1065,10 +1093,27 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
              "cc_gemm: no output");
   CC_REQUIRE(d->rms_p32 == nullptr || (d->rms_ms != nullptr && d->rms_mom != nullptr),
              "cc_gemm: fused RMSprop needs ms and mom");
+  CC_REQUIRE(d->route_world >= 0 && d->route_world <= CC_PEER_MAX, "cc_gemm: route_world=%d",
+             d->route_world);
+  if (d->route_world > 0) {
+    CC_REQUIRE(d->out32 != nullptr && d->beta32 == 0 && d->workspace == nullptr &&
+                   d->rms_p32 == nullptr,
+               "cc_gemm: a routed output needs a plain fp32 output without split-K");
+    CC_REQUIRE(d->route_shard > 0 && (d->route_shard & 7) == 0 && d->route_shard < (1ll << 32) &&
+                   d->route_off0 >= 0 && (d->route_off0 & 3) == 0,
+               "cc_gemm: route_shard=%lld route_off0=%lld", (long long)d->route_shard,
+               (long long)d->route_off0);
+    for (int q = 0; q < d->route_world; ++q)
+      CC_REQUIRE(d->route_base[q] != nullptr, "cc_gemm: route_base[%d] is null", q);
+  }
   if (g_num_sms == 0) {
     int dev = 0;
     CC_CHECK_CUDA(cudaGetDevice(&dev));
     CC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // data-parallel runs leave SMs to the NCCL kernels that overlap the backward pass: a
+    // persistent GEMM launched with more CTAs than free SMs would run a second, serial wave
+    const int cap = env_int("CC_GEMM_SMS", 0);
+    if (cap >= 2 && cap < g_num_sms) g_num_sms = cap / 2 * 2;
   }
   const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;
 
@@ -1124,7 +1169,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     splits = 1;
   }
   const bool persistent =
-      splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr);
+      splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr ||
+                      d->route_world > 0);
 
   // 2-CTA clusters (B tile multicast) whenever there are at least two row tiles
   p.cluster = (persistent && mt >= 2 && env_int("CC_GEMM_CLUSTER", 2) == 2 &&
@@ -1216,6 +1262,11 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.rms_momentum = d->rms_momentum;
   e.rms_eps = d->rms_eps;
   e.rms_cs = env_int("CC_GEMM_RMS_CS", 1);
+  e.route_world = d->route_world;
+  e.route_shard = (unsigned)d->route_shard;
+  e.route_off0 = d->route_off0;
+  for (int q = 0; q < CC_PEER_MAX; ++q)
+    e.route_base[q] = q < d->route_world ? d->route_base[q] : nullptr;
 
   if (persistent) {
     // fused optimiser on weight gradients (both operands MN-major, no epilogue math): the

@@ -39,6 +39,8 @@ _SMALL_WIDTH = int(os.environ.get("CELLCOMM_B200_SMALL_WIDTH", "512"))
 _SHARD_OPTIMIZER = os.environ.get("CELLCOMM_B200_SHARD_OPT", "1") != "0"
 # ... in buckets of about this many parameters, each reduce-scattered on the side stream as soon
 # as the backward pass has produced its gradient (big layers are cut along their rows)
+# diagnostic: data-parallel step without gradient exchange / update (compute-only lower bound)
+_DP_SKIP_UPDATE = os.environ.get("CELLCOMM_B200_DP_SKIP_UPDATE", "0") == "1"
 _BUCKET_ELEMS = int(os.environ.get("CELLCOMM_B200_BUCKET_ELEMS", str(48 << 20)))
 
 
@@ -226,6 +228,33 @@ class TorchDist:
         if self.grad_group is None:
             self.grad_group = group
 
+    def symmetric_zeros(self, numel, dtype, device):
+        """A zeroed buffer mapped into every rank's address space over NVLink (torch symmetric
+        memory; collective call) -> (tensor, [device pointer of rank q's copy], handle), or None
+        when peer memory is unavailable (CPU / gloo tests, several nodes, CELLCOMM_B200_PEER_OPT=0).
+        The peer-memory optimiser kernel (csrc/peer_optimizer.cu) is the only consumer."""
+        if (self.world_size not in (2, 4, 8) or torch.device(device).type != "cuda"
+                or os.environ.get("CELLCOMM_B200_PEER_OPT", "1") == "0"
+                or self._dist.get_backend(self.group) != "nccl"
+                or int(os.environ.get("LOCAL_WORLD_SIZE", self.world_size)) != self.world_size):
+            return None
+        if getattr(self, "_symm_failed", False):
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(int(numel), dtype=dtype, device=device)
+            t.zero_()
+            hdl = symm.rendezvous(t, self._dist.group.WORLD if self.group is None else self.group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        except Exception as exc:      # fails on every rank alike: fall back to the NCCL path
+            self._symm_failed = True
+            if self.rank == 0:
+                print(f"cellcomm_b200: symmetric memory unavailable ({exc}); data-parallel "
+                      f"updates use NCCL reduce-scatter / all-gather", flush=True)
+            return None
+        assert ptrs[self.rank] == t.data_ptr(), "symmetric memory: local pointer mismatch"
+        return t, ptrs, hdl
+
     def all_reduce(self, t):
         if self.world_size > 1:
             self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
@@ -333,10 +362,27 @@ class Net:
         # padded so that 1/world shards (world <= 16) stay 256-element aligned
         self.n_flat = max((off + 4095) // 4096 * 4096, 4096)
         self.p32 = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
-        self.g32 = torch.zeros_like(self.p32)
         self.ms = torch.zeros_like(self.p32)
         self.mom = torch.zeros_like(self.p32)
-        self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
+        # data parallel on one node: the gradient and the bf16 weights live in peer-mapped
+        # memory so that the fused optimiser kernel can read every rank's gradient and write
+        # every rank's weights directly over NVLink
+        self.peer = None
+        sym = getattr(self.dist, "symmetric_zeros", None)
+        got = None
+        if sym is not None and _SHARD_OPTIMIZER and 64 % self.dist.world_size == 0:
+            got = sym(self.n_flat * self.dist.world_size, torch.float32, dev)
+        if got is not None:
+            # stage[q] on rank r = rank q's gradient contribution for the elements r owns (the
+            # wgrad GEMM epilogues push it there); stage[r] on rank r is r's own gradient buffer
+            W, me = self.dist.world_size, self.dist.rank
+            self.stage, s_ptrs, h1 = got
+            self.g32 = self.stage[me * self.n_flat:(me + 1) * self.n_flat]
+            self.p16, w_ptrs, h2 = sym(self.n_flat, ops.COMPUTE_DTYPE, dev)
+            self.peer = {"stage": s_ptrs, "p16": w_ptrs, "handles": [h1, h2], "epoch": 0}
+        else:
+            self.g32 = torch.zeros_like(self.p32)
+            self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
         self.layers = []
         for m in meta:
             L = dict(m)
@@ -412,6 +458,14 @@ class Net:
         # gaps (alignment padding before a region, zero-width layers) carry zero gradients and
         # zero weights: they can stay out of the collectives
         self._bucket_scratch = None
+        for n, bk in enumerate(self.buckets):
+            bk["index"] = n
+        if self.peer is not None:
+            # hand-shake flags [kind: 0 ready / 1 done][bucket, last = replicated tail][source rank]
+            W, nb = self.dist.world_size, len(self.buckets) + 1
+            flags, f_ptrs, h3 = self.dist.symmetric_zeros(2 * nb * W, torch.int32, self.device)
+            self.peer.update(flags=flags, f=f_ptrs, nb=nb)
+            self.peer["handles"].append(h3)
 
     def sync_compute_copy(self):
         """bf16 compute copy <- fp32 master (after init / set_weights)."""
@@ -729,6 +783,8 @@ class Net:
         if train and self._bucketed():
             for bk in self.buckets:
                 bk["pending"], bk["launched"] = bk["pieces"], False
+            if self.peer is not None:
+                self.peer["epoch"] += 1
         out_t = g.output
         seed = self._buf(self.grad, out_t)[:rows]
         if g.widths[out_t] > 0 and dout.data_ptr() != seed.data_ptr():
@@ -788,7 +844,8 @@ class Net:
                                     a, b = pc["lo"] - ro, pc["hi"] - ro
                                     ops.dense_wgrad([p_[0][:, a:b] for p_ in pairs],
                                                     [p_[1] for p_ in pairs],
-                                                    L["dw"][pc["lo"]:pc["hi"]])
+                                                    L["dw"][pc["lo"]:pc["hi"]],
+                                                    route=self._route(pc))
                                     self._piece_done(pc)
                             else:
                                 dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
@@ -897,15 +954,22 @@ class Net:
         if bk["launched"]:
             return
         bk["launched"] = True
+        if _DP_SKIP_UPDATE:
+            return
         W, r = self.dist.world_size, self.dist.rank
         n = (bk["end"] - bk["start"]) // W
         sl = slice(bk["start"] + r * n, bk["start"] + (r + 1) * n)
-        if self._bucket_scratch is None:
+        if self._bucket_scratch is None and self.peer is None:
             biggest = max(b["end"] - b["start"] for b in self.buckets) // W
             self._bucket_scratch = torch.empty(biggest, dtype=torch.float32, device=self.device)
-        shard = self._bucket_scratch[:n]
+        shard = self._bucket_scratch[:n] if self.peer is None else None
+
+        def run_peer():
+            self._peer_update(bk["index"], bk["start"] + r * n, n, broadcast=True)
 
         def run():
+            if self.peer is not None:
+                return run_peer()
             self.dist.reduce_scatter(shard, self.g32[bk["start"]:bk["end"]])
             ops.rmsprop_step(self.p32[sl], self.p16[sl], shard, self.ms[sl], self.mom[sl], LR, RHO,
                              MOMENTUM, EPSILON)
@@ -917,6 +981,34 @@ class Net:
         self.opt_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.opt_stream):
             run()
+
+    def _flag_ptr(self, on_rank, kind, bucket, source):
+        pr = self.peer
+        return pr["f"][on_rank] + 4 * ((kind * pr["nb"] + bucket) * self.dist.world_size + source)
+
+    def _route(self, pc):
+        """cc_gemm_desc.route_* for the wgrad GEMM of gradient piece `pc`: every element goes
+        straight to the rank that owns it in the sharded update (my slot of its staging buffer)."""
+        if self.peer is None:
+            return None
+        W, me, bk = self.dist.world_size, self.dist.rank, pc["bucket"]
+        base = 4 * (me * self.n_flat + bk["start"])
+        return (W, (bk["end"] - bk["start"]) // W, pc["start"] - bk["start"],
+                [self.peer["stage"][r] + base for r in range(W)])
+
+    def _peer_update(self, bucket, start, count, broadcast):
+        """signal "my gradient of this bucket is complete" -> fused peer-memory optimiser kernel
+        -> signal "consumed / my shard is written" (csrc/peer_optimizer.cu)."""
+        pr, W, r = self.peer, self.dist.world_size, self.dist.rank
+        ops.peer_signal([self._flag_ptr(t, 0, bucket, r) for t in range(W)], pr["epoch"])
+        if broadcast:   # sharded bucket: all contributions were pushed into MY staging slots
+            grads = [pr["stage"][r] + 4 * q * self.n_flat for q in range(W)]
+        else:           # replicated tail: pull every rank's own (small) gradient
+            grads = [pr["stage"][q] + 4 * q * self.n_flat for q in range(W)]
+        ops.peer_rmsprop(W, r, grads, pr["p16"], self.p32, self.ms, self.mom, start, count,
+                         broadcast, LR, RHO, MOMENTUM, EPSILON, self._flag_ptr(r, 0, bucket, 0),
+                         pr["epoch"])
+        ops.peer_signal([self._flag_ptr(t, 1, bucket, r) for t in range(W)], pr["epoch"])
 
     def _reduce_and_update(self):
         """Data-parallel update.  world == 1: one sweep.  world > 1 (ZeRO-1 style): reduce-scatter
@@ -930,6 +1022,18 @@ class Net:
             # pass did not reach), then the replicated update of biases and BN gamma/beta
             for bk in self.buckets:
                 self._launch_bucket(bk)
+            if _DP_SKIP_UPDATE:
+                return
+            if self.peer is not None:
+                # biases + BN gamma/beta: replicated update from the sum of all ranks' gradients,
+                # then wait until every rank has consumed every bucket of this update (my
+                # gradient buffer may be rewritten, my bf16 weights are complete)
+                pr = self.peer
+                self._peer_update(pr["nb"] - 1, K, self.n_flat - K, broadcast=False)
+                ops.peer_wait(self._flag_ptr(self.dist.rank, 1, 0, 0),
+                              pr["nb"] * self.dist.world_size, pr["epoch"])
+                self._master_stale = True
+                return
             tail = slice(K, self.n_flat)
             self.dist.all_reduce_grad(self.g32[tail])
             ops.rmsprop_step(self.p32[tail], self.p16[tail], self.g32[tail], self.ms[tail],
@@ -1300,6 +1404,57 @@ class BiGanEngine:
             for L, (mm, mv) in zip([L for L in n.layers if L["kind"] == "bn"], s["bn"]):
                 L["moving_mean"].copy_(mm)
                 L["moving_var"].copy_(mv)
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything a resumed run needs, as host numpy arrays in Keras layout: per network the
+        weights in creation order (Dense kernel[in,out], bias; BatchNormalization gamma, beta,
+        moving_mean, moving_variance), the RMSprop slots (rms, momentum) of every trainable
+        tensor, plus the dropout / prior RNG stream position.  The reference has no
+        checkpointing at all; the layout is the one `Model.get_weights()` and
+        `optimizer.get_weights()` would give, so a Keras-side tool can consume it."""
+        self.join()
+        out = {"meta/variant": self.variant, "meta/encoding_size": self.Z,
+               "meta/gene_size": self.Gn, "meta/rng_seed": self.rng_seed,
+               "meta/rng_counter": int(self.rng_counter.item())}
+        for name, net in self.nets.items():
+            for i, w in enumerate(net.get_weights()):
+                out[f"{name}/w{i}"] = w
+            for i, (ms, mom) in enumerate(net.get_slots()):
+                out[f"{name}/rms{i}"] = ms
+                out[f"{name}/mom{i}"] = mom
+        return out
+
+    def load_state_dict(self, state):
+        for key, want in (("meta/variant", self.variant), ("meta/encoding_size", self.Z),
+                          ("meta/gene_size", self.Gn)):
+            got = state[key]
+            got = got.item() if hasattr(got, "item") else got
+            if str(got) != str(want):
+                raise ValueError(f"checkpoint {key} = {got}, this model has {want}")
+        for name, net in self.nets.items():
+            n_w = len([k for k in state if k.startswith(f"{name}/w")])
+            net.set_weights([state[f"{name}/w{i}"] for i in range(n_w)])   # zeroes the slots
+            n_s = len([k for k in state if k.startswith(f"{name}/rms")])
+            net.set_slots([(state[f"{name}/rms{i}"], state[f"{name}/mom{i}"]) for i in range(n_s)])
+        self.rng_seed = int(state["meta/rng_seed"])
+        self.rng_counter.fill_(int(state["meta/rng_counter"]))
+        self._graphs.clear()          # captured steps baked the old RNG seed in
+
+    def save_checkpoint(self, path):
+        """One .npz file (written atomically).  Data-parallel runs: call on every rank (the
+        sharded fp32 master weights are gathered collectively); rank 0 writes."""
+        import numpy as np
+        state = self.state_dict()
+        if self.dist.rank == 0:
+            tmp = path + ".tmp.npz"
+            np.savez(tmp, **state)
+            os.replace(tmp, path)
+
+    def load_checkpoint(self, path):
+        import numpy as np
+        with np.load(path, allow_pickle=False) as f:
+            self.load_state_dict({k: f[k] for k in f.files})
 
     def join(self):
         """Order the current stream after every pending side-stream optimiser update (call

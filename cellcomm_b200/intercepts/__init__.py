@@ -7,6 +7,7 @@ from datetime import datetime
 from .plot_intercepts import PlotIntercepts
 from .sink_intercepts import SinkIntercepts
 from .db_recorder import DbRecorder
+from .encoding_files import EncodingFiles
 
 
 def combined_interceptors(interceptors):

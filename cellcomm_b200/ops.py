@@ -78,7 +78,7 @@ def launch_count():
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
          alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
-         rms=None):
+         rms=None, route=None):
     lib = _lib.load()
     d = GemmDesc()
     d.M, d.N = int(M), int(N)
@@ -117,6 +117,14 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
         d.rms_ld = _ld(p32)
         d.rms_lr, d.rms_rho, d.rms_momentum, d.rms_eps = float(lr), float(rho), float(momentum), \
             float(eps)
+    if route is not None:
+        world, shard, off0, bases = route
+        if out32 is None or beta32:
+            raise ValueError("gemm(route=...): needs a plain fp32 output")
+        d.route_world, d.route_shard, d.route_off0 = int(world), int(shard), int(off0)
+        for q in range(world):
+            d.route_base[q] = int(bases[q])
+        d.workspace, d.workspace_elems = None, 0       # routed tiles are never split along K
     check(lib.cc_gemm(C.byref(d), _stream()))
 
 
@@ -144,7 +152,7 @@ def dense_dgrad(dzs, ws16, out, *, dact_y=None, dact=0, alpha=1.0, beta=0):
          **kw)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
     """dw32[K,N] (+)= x[M,K]^T @ dz[M,N].  x may be a list [hi, lo] (bf16 expansion): the
     terms accumulate as GEMM segments along the batch reduction.
     rms = (p32, p16, ms, mom, lr, rho, momentum, eps): fuse the Keras RMSprop update of that
@@ -155,8 +163,10 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None):
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
     # tiny layers (one or two output tiles, reduction over the whole batch) take the split-K
     # path; the fused-optimiser epilogue cannot be split
+    # route = (world, shard, off0, bases): the epilogue stores every element of dw32 to the rank
+    # that owns it in the sharded optimiser (see cc_gemm_desc.route_*)
     gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta,
-         use_ws=rms is None, rms=rms)
+         use_ws=rms is None and route is None, rms=rms, route=route)
 
 
 # --------------------------------------------------------------------------- data
@@ -367,3 +377,33 @@ def bias_act(bias, act, rows, out16=None, out32=None):
 
 def fill_f32(t, value):
     check(_lib.load().cc_fill_f32(_p(t), float(value), t.numel(), _stream()))
+
+
+# --------------------------------------------------------------------------- peer-memory optimiser
+def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, broadcast, lr, rho,
+                 momentum, eps, ready_ptr, epoch):
+    """Fused reduce-scatter -> Keras RMSprop -> bf16 all-gather over NVLink peer memory for the
+    flat element range [start, start+count).  grad_ptrs / p16_ptrs: device pointers (ints) of
+    every rank's flat gradient / bf16 weight buffer; p32, ms, mom: this rank's flat buffers."""
+    for t, name in ((p32, "p32"), (ms, "ms"), (mom, "mom")):
+        _req(t, torch.float32, name)
+    d = _lib.PeerRmspropDesc()
+    d.world, d.rank = int(world), int(rank)
+    for q in range(world):
+        d.grad[q], d.p16[q] = int(grad_ptrs[q]), int(p16_ptrs[q])
+    d.p32, d.ms, d.mom = p32.data_ptr(), ms.data_ptr(), mom.data_ptr()
+    d.start, d.count, d.broadcast = int(start), int(count), int(bool(broadcast))
+    d.lr, d.rho, d.momentum, d.eps = float(lr), float(rho), float(momentum), float(eps)
+    d.ready, d.epoch = int(ready_ptr), int(epoch) & 0xFFFFFFFF
+    check(_lib.load().cc_peer_rmsprop(C.byref(d), _stream()))
+
+
+def peer_signal(target_ptrs, value):
+    """After everything this stream has done so far, store `value` to every flag address."""
+    arr = (C.c_void_p * len(target_ptrs))(*[int(p) for p in target_ptrs])
+    check(_lib.load().cc_peer_signal(arr, len(target_ptrs), int(value) & 0xFFFFFFFF, _stream()))
+
+
+def peer_wait(flags_ptr, n, value):
+    """Block the stream until n consecutive local uint32 flags are >= value."""
+    check(_lib.load().cc_peer_wait(int(flags_ptr), int(n), int(value) & 0xFFFFFFFF, _stream()))

@@ -145,6 +145,17 @@ typedef struct cc_gemm_desc {
   void* rms_p16;
   int64_t rms_ld;
   float rms_lr, rms_rho, rms_momentum, rms_eps;
+  /* optional routed fp32 output (data-parallel weight-gradient GEMMs): the GEMM itself performs
+   * the reduce-scatter's data movement.  The output lies in a gradient bucket of the flat
+   * parameter layout that is sharded evenly over route_world ranks; element `rel` (offset from
+   * the bucket start, = route_off0 + row*ld32 + col) belongs to rank rel / route_shard and is
+   * stored to route_base[owner] + rel -- this rank's slot in the OWNER's staging buffer, a
+   * peer-mapped pointer over NVLink (the own share goes to local memory).  out32 must be set
+   * (it is the local address of element (0,0)); beta32 and split-K are not available. */
+  int32_t route_world;   /* 0: off */
+  int64_t route_shard;   /* elements per rank, multiple of 8 */
+  int64_t route_off0;    /* offset of out32[0,0] from the bucket start, multiple of 4 */
+  float* route_base[16];
 } cc_gemm_desc;
 
 int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);
@@ -295,6 +306,41 @@ int cc_argmax_onehot(const float* p32, int64_t ldp, void* out16, int64_t ldo, fl
 int cc_rmsprop_step(float* p32, void* p16, const float* g, float* ms, float* mom, int64_t rows,
                     int64_t cols, int64_t ld, float lr, float rho, float momentum, float eps,
                     float grad_scale, cc_stream_t stream);
+
+/* ---- data-parallel optimiser step over NVLink peer memory (csrc/peer_optimizer.cu) --------
+ * One process per GPU on one node; every rank's flat gradient buffer and bf16 weight buffer
+ * are mapped into every process (torch symmetric memory / CUDA IPC does the mapping, the
+ * library only sees device pointers).  cc_peer_rmsprop fuses
+ *     reduce-scatter (P2P loads) -> Keras RMSprop on this rank's shard -> all-gather of the
+ *     bf16 weights (P2P stores)
+ * for the element range [start, start+count) of the flat buffers.  The reference has no
+ * counterpart (single process); under data parallelism this is the gradient exchange around
+ * `optimizer.apply_gradients` of src/bigan_classify.py:88,144-155.
+ *   grad[q], p16[q] : rank q's buffers (q < world), the same flat layout on every rank
+ *   broadcast = 1   : sharded update, bf16 result stored to all ranks;
+ *   broadcast = 0   : replicated update (biases / BN parameters): every rank updates the
+ *                     whole range from the sum of all gradients, local stores only
+ *   ready[q]        : LOCAL flags; the kernel starts once ready[q] >= epoch for all q
+ * cc_peer_signal stores `value` to n remote/local flags after a system-scope fence (everything
+ * the stream did before is visible to the peers first); cc_peer_wait blocks the stream until
+ * n consecutive local flags are >= value.  Epochs are compared modulo 2^32. */
+#define CC_PEER_MAX 16
+typedef struct cc_peer_rmsprop_desc {
+  int32_t world, rank;
+  const float* grad[CC_PEER_MAX];
+  void* p16[CC_PEER_MAX];
+  float* p32;
+  float* ms;
+  float* mom;
+  int64_t start, count;
+  int32_t broadcast;
+  float lr, rho, momentum, eps;
+  const uint32_t* ready;
+  uint32_t epoch;
+} cc_peer_rmsprop_desc;
+int cc_peer_rmsprop(const cc_peer_rmsprop_desc* desc, cc_stream_t stream);
+int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value, cc_stream_t stream);
+int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, cc_stream_t stream);
 
 /* Dense layer with zero input width: y[r,c] = act(bias[c]).  The reference's 5-gene fixture
  * produces Dense(0) layers (int(5*0.1) == 0; src/bigan_cont.py:8,29) whose consumers see K=0. */

@@ -68,7 +68,8 @@ def dense_dgrad(dzs, ws16, out16, *, dact_y=None, dact=0, alpha=1.0, beta=0):
     _store(out16, acc.float(), beta)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
+    assert route is None, "routed outputs need peer memory (GPU only)"
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
     acc = 0

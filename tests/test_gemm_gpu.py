@@ -281,3 +281,33 @@ def test_effective_tile_width_auto_matches_full_width(monkeypatch):
         outs.append(o.cpu())
     assert torch.equal(outs[0], outs[1])
     _check(outs[0], a.float() @ b.float(), K, False)
+
+
+def test_routed_wgrad_output_two_ranks_emulated():
+    """cc_gemm_desc.route_*: the wgrad epilogue stores every element of dW to the staging
+    buffer of the rank that owns it in the sharded optimiser (here both "ranks" live on one
+    device).  Bucket = this GEMM's rows plus a neighbouring region before it; the shard
+    boundary falls in the middle of a row."""
+    ops = _ops()
+    M, N, K = 300, 200, 192                     # dW[M, N] = X[K, M]^T dZ[K, N]
+    ld = ops.pad_ld(N)                          # 256
+    a, b = _rand(K, M, 41), _rand(K, N, 42)
+    da, db = _dev2d(a, ops), _dev2d(b, ops)
+    before = 1024                               # elements of the bucket ahead of this piece
+    total = before + M * ld
+    W = 2
+    shard = (total // W + 7) // 8 * 8           # owner boundary inside row (shard-before)//ld
+    stage = [torch.full((total,), float("nan"), device="cuda") for _ in range(W)]
+    local = stage[0][before:].view(M, ld)[:, :N]            # "my" gradient view (rank 0 = me)
+    ops.dense_wgrad([da], [db], local, route=(W, shard, before, [t.data_ptr() for t in stage]))
+    torch.cuda.synchronize()
+    ref = torch.full((M, ld), float("nan"))
+    ref[:, :N] = a.float().t() @ b.float()
+    flat_ref = torch.cat([torch.full((before,), float("nan")), ref.flatten()])
+    owner = torch.clamp(torch.arange(total) // shard, max=W - 1)
+    for r in range(W):
+        got = stage[r].cpu()
+        mine = (owner == r) & ~torch.isnan(flat_ref)
+        assert torch.isnan(got[~mine]).all(), f"rank {r}: wrote outside its share"
+        assert torch.allclose(got[mine], flat_ref[mine], rtol=1e-4, atol=2e-3 * K ** 0.5)
+    assert (owner == 1).any() and ((owner == 0) & ~torch.isnan(flat_ref)).any()

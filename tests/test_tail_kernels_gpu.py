@@ -300,3 +300,80 @@ def test_fp32_operands_bias_grad_and_split():
     dw = torch.empty(K, N, device="cuda")
     ops.dense_wgrad([xh, xl], dzz, dw)
     assert torch.allclose(dw, xw.t() @ dzz.float(), rtol=1e-3, atol=2e-3)
+
+
+def test_peer_rmsprop_two_ranks_emulated_on_one_gpu():
+    """csrc/peer_optimizer.cu with both "ranks" on one device: every rank sums both gradient
+    buffers (P2P loads), updates its shard of the fp32 master / slots and stores the bf16
+    result into BOTH weight buffers; the flags order signal -> kernel -> signal -> wait.
+    Reference: Keras RMSprop(momentum) on the summed gradient, fp32."""
+    import torch
+    from cellcomm_b200 import ops
+    n, W = 4096, 2
+    lr, rho, mu, eps = 0.0075, 0.85, 0.1, 1e-7
+    g = torch.Generator(device="cuda").manual_seed(3)
+    grads = [torch.randn(n, device="cuda", generator=g) for _ in range(W)]
+    p32 = [torch.randn(n, device="cuda", generator=g) for _ in range(W)]
+    p32[1].copy_(p32[0])                                  # replicas start identical
+    ms = [torch.rand(n, device="cuda", generator=g) for _ in range(W)]
+    ms[1].copy_(ms[0])
+    mom = [torch.randn(n, device="cuda", generator=g) * 0.01 for _ in range(W)]
+    mom[1].copy_(mom[0])
+    p16 = [torch.zeros(n, dtype=torch.bfloat16, device="cuda") for _ in range(W)]
+    flags = [torch.zeros(2 * 2 * W, dtype=torch.int32, device="cuda") for _ in range(W)]
+    w0, s0, m0 = p32[0].clone(), ms[0].clone(), mom[0].clone()
+
+    def fptr(on, kind, bucket, src):
+        return flags[on].data_ptr() + 4 * ((kind * 2 + bucket) * W + src)
+
+    epoch, start, count = 1, 64, n - 128                  # a sub-range; the rest must not move
+    half = count // W
+    # one stream plays both ranks in protocol order (two spinning kernels on one device could
+    # be serialised onto one hardware queue): ready signals, kernels, done signals, waits
+    for r in range(W):
+        ops.peer_signal([fptr(t, 0, 0, r) for t in range(W)], epoch)
+    for r in range(W):
+        ops.peer_rmsprop(W, r, [t.data_ptr() for t in grads], [t.data_ptr() for t in p16],
+                         p32[r], ms[r], mom[r], start + r * half, half, True, lr, rho, mu, eps,
+                         fptr(r, 0, 0, 0), epoch)
+        ops.peer_signal([fptr(t, 1, 0, r) for t in range(W)], epoch)
+    for r in range(W):
+        ops.peer_wait(fptr(r, 1, 0, 0), W, epoch)
+    torch.cuda.synchronize()
+    gsum = grads[0] + grads[1]
+    s_ref = rho * s0 + (1 - rho) * gsum * gsum
+    m_ref = mu * m0 + lr * gsum / torch.sqrt(s_ref + eps)
+    w_ref = w0 - m_ref
+    for r in range(W):
+        sl = slice(start + r * half, start + (r + 1) * half)
+        assert torch.allclose(ms[r][sl], s_ref[sl], rtol=1e-5, atol=1e-7)
+        assert torch.allclose(mom[r][sl], m_ref[sl], rtol=2e-4, atol=1e-7)
+        assert torch.allclose(p32[r][sl], w_ref[sl], rtol=1e-5, atol=1e-6)
+        other = slice(start + (1 - r) * half, start + (2 - r) * half)
+        assert torch.equal(p32[r][other], w0[other])      # the peer's shard is not mine to touch
+        assert torch.equal(p32[r][:start], w0[:start]) and torch.equal(p32[r][start + count:], w0[start + count:])
+    # both weight buffers hold bf16(updated master) over the whole range, bit-identical
+    full = torch.cat([p32[0][start:start + half], p32[1][start + half:start + count]])
+    assert torch.equal(p16[0][start:start + count], full.to(torch.bfloat16))
+    assert torch.equal(p16[0], p16[1])
+    assert torch.count_nonzero(p16[0][:start]) == 0
+
+
+def test_peer_rmsprop_replicated_tail():
+    """broadcast = 0 (biases / BN parameters): every rank updates the whole range from the sum
+    of all gradients and stores only its own bf16 copy."""
+    import torch
+    from cellcomm_b200 import ops
+    n, W = 512, 2
+    grads = [torch.full((n,), 0.5, device="cuda"), torch.full((n,), 1.5, device="cuda")]
+    p32, ms, mom = torch.ones(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p16 = [torch.zeros(n, dtype=torch.bfloat16, device="cuda") for _ in range(W)]
+    flags = torch.full((W,), 7, dtype=torch.int32, device="cuda")      # already signalled
+    ops.peer_rmsprop(W, 1, [t.data_ptr() for t in grads], [t.data_ptr() for t in p16], p32, ms, mom,
+                     0, n, False, 0.0075, 0.85, 0.1, 1e-7, flags.data_ptr(), 7)
+    torch.cuda.synchronize()
+    s = 0.15 * 4.0
+    w = 1.0 - 0.0075 * 2.0 / (s + 1e-7) ** 0.5
+    assert torch.allclose(p32, torch.full_like(p32, w), rtol=1e-5)
+    assert torch.equal(p16[1], p32.to(torch.bfloat16))
+    assert torch.count_nonzero(p16[0]) == 0               # rank 0's copy is rank 0's job

@@ -1,0 +1,23 @@
+#!/bin/bash
+# N-GPU data-parallel A/B runs of bench.py (train numbers only)
+# usage: tools/dp_sweep.sh NGPU OUT_PREFIX
+N=${1:-2}; OUT=${2:-gpurun_out/dp_sweep}
+port=29600
+run() {  # label, env...
+  label=$1; shift
+  port=$((port+1))
+  env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port $port bench.py --gpus $N --steps 8 --warmup 3 --no-roofline > ${OUT}_${label}.json 2> ${OUT}_${label}.err
+  python - "$label" "${OUT}_${label}.json" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    print(sys.argv[1], "ms/step", round(d["ms_per_step"],2), "cells/s", round(d["value"]), "e2e", round(d["e2e"]["value"]))
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+}
+run peer_sync_2 CELLCOMM_B200_ASYNC_OPT=0 CC_PEER_BLOCKS_PER_SM=2
+run peer_sync_8 CELLCOMM_B200_ASYNC_OPT=0 CC_PEER_BLOCKS_PER_SM=8
+run peer_async_8 CC_PEER_BLOCKS_PER_SM=8
+run peer_async_4 CC_PEER_BLOCKS_PER_SM=4
