@@ -46,6 +46,7 @@ class PeerRmspropDesc(C.Structure):
         ("broadcast", c_i32),
         ("lr", c_f32), ("rho", c_f32), ("momentum", c_f32), ("eps", c_f32),
         ("ready", vp), ("epoch", c_u32),
+        ("p16_multicast", vp),
     ]
 
 

@@ -672,7 +672,8 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false,
           int CLUSTER = 1>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
-gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps, const GemmParams p,
+gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
+                               const __grid_constant__ GemmParams p,
                                const int tiles_m, const int tiles_n) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;

@@ -54,7 +54,7 @@ peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
                     float* __restrict__ ms, float* __restrict__ mom, const long long start,
                     const long long count, const int broadcast, const float lr, const float rho,
                     const float momentum, const float eps, const uint32_t* ready,
-                    const uint32_t epoch) {
+                    const uint32_t epoch, bf16* __restrict__ p16_mc) {
   // every rank's gradient for this bucket must be complete (and, because the flags are only
   // raised after the producing wgrad GEMMs, every rank has finished READING the old weights)
   if (threadIdx.x < world) wait_flag(ready + threadIdx.x, epoch, 1);
@@ -107,7 +107,13 @@ peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
       u.z = *reinterpret_cast<uint32_t*>(&h2);
       u.w = *reinterpret_cast<uint32_t*>(&h3);
     }
-    if (broadcast) {
+    if (broadcast && p16_mc != nullptr) {
+      // NVLS: one store to the multicast mapping, the switch replicates it to every rank
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p16_mc + off),
+                   "f"(__uint_as_float(u.x)), "f"(__uint_as_float(u.y)), "f"(__uint_as_float(u.z)),
+                   "f"(__uint_as_float(u.w))
+                   : "memory");
+    } else if (broadcast) {
       for (int q = 0; q < world; ++q) *reinterpret_cast<uint4*>(pp.p16[q] + off) = u;
     } else {
       *reinterpret_cast<uint4*>(pp.p16[0] + off) = u;   // replicated update: local copy only
@@ -166,7 +172,7 @@ extern "C" int cc_peer_rmsprop(const cc_peer_rmsprop_desc* d, cc_stream_t stream
   if (blocks > cap) blocks = cap;
   peer_rmsprop_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       pp, d->world, d->p32, d->ms, d->mom, d->start, d->count, d->broadcast, d->lr, d->rho,
-      d->momentum, d->eps, d->ready, d->epoch);
+      d->momentum, d->eps, d->ready, d->epoch, (bf16*)d->p16_multicast);
   CC_CHECK_LAUNCH();
   return 0;
 }

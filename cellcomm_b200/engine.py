@@ -379,7 +379,14 @@ class Net:
             self.stage, s_ptrs, h1 = got
             self.g32 = self.stage[me * self.n_flat:(me + 1) * self.n_flat]
             self.p16, w_ptrs, h2 = sym(self.n_flat, ops.COMPUTE_DTYPE, dev)
-            self.peer = {"stage": s_ptrs, "p16": w_ptrs, "handles": [h1, h2], "epoch": 0}
+            mc = 0
+            if os.environ.get("CELLCOMM_B200_MULTICAST", "1") != "0":
+                try:
+                    mc = int(h2.multicast_ptr or 0)     # NVSwitch multimem mapping (0: none)
+                except Exception:
+                    mc = 0
+            self.peer = {"stage": s_ptrs, "p16": w_ptrs, "p16_mc": mc, "handles": [h1, h2],
+                         "epoch": 0}
         else:
             self.g32 = torch.zeros_like(self.p32)
             self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
@@ -1007,7 +1014,7 @@ class Net:
             grads = [pr["stage"][q] + 4 * q * self.n_flat for q in range(W)]
         ops.peer_rmsprop(W, r, grads, pr["p16"], self.p32, self.ms, self.mom, start, count,
                          broadcast, LR, RHO, MOMENTUM, EPSILON, self._flag_ptr(r, 0, bucket, 0),
-                         pr["epoch"])
+                         pr["epoch"], p16_multicast=pr["p16_mc"])
         ops.peer_signal([self._flag_ptr(t, 1, bucket, r) for t in range(W)], pr["epoch"])
 
     def _reduce_and_update(self):

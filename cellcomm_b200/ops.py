@@ -381,7 +381,7 @@ def fill_f32(t, value):
 
 # --------------------------------------------------------------------------- peer-memory optimiser
 def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, broadcast, lr, rho,
-                 momentum, eps, ready_ptr, epoch):
+                 momentum, eps, ready_ptr, epoch, p16_multicast=0):
     """Fused reduce-scatter -> Keras RMSprop -> bf16 all-gather over NVLink peer memory for the
     flat element range [start, start+count).  grad_ptrs / p16_ptrs: device pointers (ints) of
     every rank's flat gradient / bf16 weight buffer; p32, ms, mom: this rank's flat buffers."""
@@ -395,6 +395,7 @@ def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, b
     d.start, d.count, d.broadcast = int(start), int(count), int(bool(broadcast))
     d.lr, d.rho, d.momentum, d.eps = float(lr), float(rho), float(momentum), float(eps)
     d.ready, d.epoch = int(ready_ptr), int(epoch) & 0xFFFFFFFF
+    d.p16_multicast = int(p16_multicast) or None
     check(_lib.load().cc_peer_rmsprop(C.byref(d), _stream()))
 
 

@@ -321,6 +321,8 @@ int cc_rmsprop_step(float* p32, void* p16, const float* g, float* ms, float* mom
  *   broadcast = 0   : replicated update (biases / BN parameters): every rank updates the
  *                     whole range from the sum of all gradients, local stores only
  *   ready[q]        : LOCAL flags; the kernel starts once ready[q] >= epoch for all q
+ *   grad[q]         : in the push design (cc_gemm_desc.route_*) these are this rank's LOCAL
+ *                     staging slots, already filled by every rank's wgrad GEMM epilogues
  * cc_peer_signal stores `value` to n remote/local flags after a system-scope fence (everything
  * the stream did before is visible to the peers first); cc_peer_wait blocks the stream until
  * n consecutive local flags are >= value.  Epochs are compared modulo 2^32. */
@@ -337,6 +339,11 @@ typedef struct cc_peer_rmsprop_desc {
   float lr, rho, momentum, eps;
   const uint32_t* ready;
   uint32_t epoch;
+  /* optional NVLS multicast address of the bf16 weight buffer (NVSwitch multimem mapping of
+   * the same symmetric allocation): with broadcast = 1 ONE multimem.st per 16 bytes delivers
+   * the updated weights to every rank, instead of world P2P stores (7/8 less NVLink egress
+   * for the all-gather at 8 GPUs).  NULL: P2P stores. */
+  void* p16_multicast;
 } cc_peer_rmsprop_desc;
 int cc_peer_rmsprop(const cc_peer_rmsprop_desc* desc, cc_stream_t stream);
 int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value, cc_stream_t stream);

@@ -43,5 +43,9 @@ for name, n in e.nets.items():
     dist.broadcast(refbn, src=0)
     assert torch.equal(bn, refbn), f"rank {rank}: {name} BN stats differ"
 if rank == 0:
-    print(f"dp_check ok: world={world} losses={losses}")
+    pr = e.G.peer
+    mode = "NCCL reduce-scatter / all-gather" if pr is None else (
+        "peer-memory push + fused optimiser, all-gather by " +
+        ("NVLS multicast stores" if pr["p16_mc"] else "P2P stores"))
+    print(f"dp_check ok: world={world} losses={losses} [{mode}]")
 dist.destroy_process_group()

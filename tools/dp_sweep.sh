@@ -11,13 +11,11 @@ run() {  # label, env...
   python - "$label" "${OUT}_${label}.json" <<'PY'
 import json,sys
 try:
-    d=json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
+    d=json.loads([l for l in open(sys.argv[2]).read().splitlines() if l.startswith("{")][-1])
     print(sys.argv[1], "ms/step", round(d["ms_per_step"],2), "cells/s", round(d["value"]), "e2e", round(d["e2e"]["value"]))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run peer_sync_2 CELLCOMM_B200_ASYNC_OPT=0 CC_PEER_BLOCKS_PER_SM=2
-run peer_sync_8 CELLCOMM_B200_ASYNC_OPT=0 CC_PEER_BLOCKS_PER_SM=8
-run peer_async_8 CC_PEER_BLOCKS_PER_SM=8
-run peer_async_4 CC_PEER_BLOCKS_PER_SM=4
+run multicast A=1
+run p2p_stores CELLCOMM_B200_MULTICAST=0
