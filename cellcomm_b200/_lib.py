@@ -111,6 +111,8 @@ SIGNATURES = {
     "cc_peer_rmsprop": (C.c_int, [C.POINTER(PeerRmspropDesc), vp]),
     "cc_peer_signal": (C.c_int, [C.POINTER(vp), c_i32, c_u32, vp]),
     "cc_peer_wait": (C.c_int, [vp, c_i32, c_u32, vp]),
+    "cc_peer_allreduce": (C.c_int, [vp, c_i32, c_i32, c_i32, C.POINTER(vp), C.POINTER(vp), c_i64,
+                                    c_u32, vp]),
 }
 
 

@@ -255,9 +255,36 @@ class TorchDist:
         assert ptrs[self.rank] == t.data_ptr(), "symmetric memory: local pointer mismatch"
         return t, ptrs, hdl
 
+    _AR_CAP = 16384      # floats per small all-reduce over peer memory (largest BN: 2 x 6738)
+
+    def _peer_allreduce_state(self, device):
+        """Peer-mapped staging slots + flags for the one-kernel small all-reduce (lazy,
+        collective: the first all-reduce happens at the same point on every rank)."""
+        st = getattr(self, "_ar", None)
+        if st is None:
+            st = False
+            if os.environ.get("CELLCOMM_B200_PEER_ALLREDUCE", "1") != "0":
+                W = self.world_size
+                a = self.symmetric_zeros(2 * W * self._AR_CAP, torch.float32, device)
+                if a is not None:
+                    b = self.symmetric_zeros(W, torch.int32, device)
+                    st = {"slots": a[1], "flags": b[1], "keep": (a, b), "epoch": 0}
+            self._ar = st
+        return st or None
+
     def all_reduce(self, t):
+        """Sum all-reduce of a small tensor (BN statistics, loss buffer)."""
         if self.world_size > 1:
-            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+            st = None
+            if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and \
+                    t.numel() <= self._AR_CAP:
+                st = self._peer_allreduce_state(t.device)
+            if st is not None:
+                st["epoch"] += 1
+                ops.peer_allreduce(t, self.world_size, self.rank, st["slots"], st["flags"],
+                                   self._AR_CAP, st["epoch"])
+            else:
+                self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
     def all_reduce_grad(self, t):

@@ -408,3 +408,14 @@ def peer_signal(target_ptrs, value):
 def peer_wait(flags_ptr, n, value):
     """Block the stream until n consecutive local uint32 flags are >= value."""
     check(_lib.load().cc_peer_wait(int(flags_ptr), int(n), int(value) & 0xFFFFFFFF, _stream()))
+
+
+def peer_allreduce(data, world, rank, slot_ptrs, flag_ptrs, cap, epoch):
+    """In-place sum all-reduce of a small contiguous fp32 tensor over peer memory (one kernel)."""
+    _req(data, torch.float32, "data")
+    if not data.is_contiguous():
+        raise ValueError("peer_allreduce: data must be contiguous")
+    sl = (C.c_void_p * world)(*[int(p) for p in slot_ptrs])
+    fl = (C.c_void_p * world)(*[int(p) for p in flag_ptrs])
+    check(_lib.load().cc_peer_allreduce(data.data_ptr(), data.numel(), int(world), int(rank), sl, fl,
+                                        int(cap), int(epoch) & 0xFFFFFFFF, _stream()))

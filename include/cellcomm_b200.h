@@ -348,6 +348,12 @@ typedef struct cc_peer_rmsprop_desc {
 int cc_peer_rmsprop(const cc_peer_rmsprop_desc* desc, cc_stream_t stream);
 int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value, cc_stream_t stream);
 int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, cc_stream_t stream);
+/* In-place sum all-reduce of n <= cap floats over peer memory in one kernel (BatchNorm batch
+ * statistics, BN-backward sums, loss buffer).  slots[q]: rank q's [2][world][cap] staging array,
+ * flags[q]: rank q's [world] flags (both peer-mapped); epoch grows by one per call, identically
+ * on every rank.  Sums in rank order, so every rank gets bit-identical results. */
+int cc_peer_allreduce(float* data, int32_t n, int32_t world, int32_t rank, float* const* slots,
+                      uint32_t* const* flags, int64_t cap, uint32_t epoch, cc_stream_t stream);
 
 /* Dense layer with zero input width: y[r,c] = act(bias[c]).  The reference's 5-gene fixture
  * produces Dense(0) layers (int(5*0.1) == 0; src/bigan_cont.py:8,29) whose consumers see K=0. */
