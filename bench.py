@@ -282,7 +282,7 @@ def run_ours(args):
     e.reserve(B)
 
     graphed = None
-    if args.graph and world == 1:
+    if args.graph and e.peer_graphable():     # one GPU, or the peer-memory data-parallel path
         graphed = e.capture_step((rowptr, colidx, values), args.genes, B,
                                  latents="host" if classify else "device")
     # classify prior: one-hot of a uniform category (src/bigan_classify.py:117-119), resident pool

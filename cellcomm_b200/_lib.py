@@ -46,6 +46,7 @@ class PeerRmspropDesc(C.Structure):
         ("broadcast", c_i32),
         ("lr", c_f32), ("rho", c_f32), ("momentum", c_f32), ("eps", c_f32),
         ("ready", vp), ("epoch", c_u32),
+        ("epoch_ctr", vp),
         ("p16_multicast", vp),
     ]
 
@@ -109,10 +110,10 @@ SIGNATURES = {
     "cc_bias_act": (C.c_int, [vp, c_i32, vp, c_i64, vp, c_i64, c_i64, c_i64, vp]),
     "cc_fill_f32": (C.c_int, [vp, c_f32, c_i64, vp]),
     "cc_peer_rmsprop": (C.c_int, [C.POINTER(PeerRmspropDesc), vp]),
-    "cc_peer_signal": (C.c_int, [C.POINTER(vp), c_i32, c_u32, vp]),
-    "cc_peer_wait": (C.c_int, [vp, c_i32, c_u32, vp]),
+    "cc_peer_signal": (C.c_int, [C.POINTER(vp), c_i32, c_u32, vp, vp]),
+    "cc_peer_wait": (C.c_int, [vp, c_i32, c_u32, vp, c_i32, vp]),
     "cc_peer_allreduce": (C.c_int, [vp, c_i32, c_i32, c_i32, C.POINTER(vp), C.POINTER(vp), c_i64,
-                                    c_u32, vp]),
+                                    c_u32, vp, vp]),
 }
 
 

@@ -122,7 +122,7 @@ class ClassifyCellBiGan(BasicBiGan):
         encodings = self.random_encoding_vector(batch_size)
         noise = self.random_uniform_vector(batch_size)
         if (isinstance(batch, CellBatch) and eng.device.type == "cuda" and
-                eng.dist.world_size == 1 and os.environ.get("CELLCOMM_B200_GRAPH", "1") != "0"):
+                eng.peer_graphable() and os.environ.get("CELLCOMM_B200_GRAPH", "1") != "0"):
             # single GPU: the whole step (gather + ~850 kernels) is one CUDA-graph launch
             gs = eng.capture_step(batch.matrix.device_csr(eng.device), batch.matrix.shape[1],
                                   batch_size, latents="host")

@@ -54,7 +54,10 @@ peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
                     float* __restrict__ ms, float* __restrict__ mom, const long long start,
                     const long long count, const int broadcast, const float lr, const float rho,
                     const float momentum, const float eps, const uint32_t* ready,
-                    const uint32_t epoch, bf16* __restrict__ p16_mc) {
+                    const uint32_t epoch_rel, const uint32_t* __restrict__ epoch_ctr,
+                    bf16* __restrict__ p16_mc) {
+  // epochs: host value, or (CUDA-graph friendly) a device counter plus a constant
+  const uint32_t epoch = epoch_rel + (epoch_ctr ? *epoch_ctr : 0u);
   // every rank's gradient for this bucket must be complete (and, because the flags are only
   // raised after the producing wgrad GEMMs, every rank has finished READING the old weights)
   if (threadIdx.x < world) wait_flag(ready + threadIdx.x, epoch, 1);
@@ -126,13 +129,21 @@ struct FlagPtrs {
 };
 
 // after everything this stream has written so far: *targets[q] = value for every q
-__global__ void peer_signal_kernel(const FlagPtrs f, const int n, const uint32_t value) {
+__global__ void peer_signal_kernel(const FlagPtrs f, const int n, const uint32_t value_rel,
+                                   const uint32_t* __restrict__ epoch_ctr) {
+  const uint32_t value = value_rel + (epoch_ctr ? *epoch_ctr : 0u);
   __threadfence_system();
   if (threadIdx.x < n) st_release_sys(f.t[threadIdx.x], value);
 }
 
-__global__ void peer_wait_kernel(const uint32_t* flags, const int n, const uint32_t value) {
+// bump != 0: the counter advances to the awaited epoch once every flag has arrived (the last
+// kernel of an update on its stream; the next update's kernels then see the new base)
+__global__ void peer_wait_kernel(const uint32_t* flags, const int n, const uint32_t value_rel,
+                                 uint32_t* epoch_ctr, const int bump) {
+  const uint32_t value = value_rel + (epoch_ctr ? *epoch_ctr : 0u);
   for (int i = threadIdx.x; i < n; i += blockDim.x) wait_flag(flags + i, value, 2);
+  __syncthreads();
+  if (bump && epoch_ctr != nullptr && threadIdx.x == 0) *epoch_ctr = value;
 }
 
 }  // namespace cc
@@ -172,24 +183,25 @@ extern "C" int cc_peer_rmsprop(const cc_peer_rmsprop_desc* d, cc_stream_t stream
   if (blocks > cap) blocks = cap;
   peer_rmsprop_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       pp, d->world, d->p32, d->ms, d->mom, d->start, d->count, d->broadcast, d->lr, d->rho,
-      d->momentum, d->eps, d->ready, d->epoch, (bf16*)d->p16_multicast);
+      d->momentum, d->eps, d->ready, d->epoch, d->epoch_ctr, (bf16*)d->p16_multicast);
   CC_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value,
-                              cc_stream_t stream) {
+                              const uint32_t* epoch_ctr, cc_stream_t stream) {
   CC_REQUIRE(n >= 1 && n <= CC_PEER_MAX, "cc_peer_signal: n=%d", n);
   FlagPtrs f;
   for (int q = 0; q < CC_PEER_MAX; ++q) f.t[q] = q < n ? targets[q] : nullptr;
-  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n, value);
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n, value, epoch_ctr);
   CC_CHECK_LAUNCH();
   return 0;
 }
 
-extern "C" int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, cc_stream_t stream) {
+extern "C" int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, uint32_t* epoch_ctr,
+                            int32_t bump, cc_stream_t stream) {
   if (n <= 0) return 0;
-  peer_wait_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(flags, n, value);
+  peer_wait_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(flags, n, value, epoch_ctr, bump);
   CC_CHECK_LAUNCH();
   return 0;
 }
@@ -212,7 +224,9 @@ struct ArPtrs {
 
 __global__ void __launch_bounds__(1024)
 peer_allreduce_kernel(const ArPtrs ap, const int world, const int rank, float* __restrict__ data,
-                      const int n, const long long cap, const uint32_t epoch) {
+                      const int n, const long long cap, const uint32_t epoch_rel,
+                      uint32_t* epoch_ctr) {
+  const uint32_t epoch = epoch_rel + (epoch_ctr ? *epoch_ctr : 0u);
   const long long par = (long long)(epoch & 1u) * world * cap;
   // 1. my contribution into slot [parity][rank] of every rank (own copy included)
   for (int q = 0; q < world; ++q) {
@@ -234,13 +248,15 @@ peer_allreduce_kernel(const ArPtrs ap, const int world, const int rank, float* _
     for (int q = 0; q < world; ++q) s += __ldcv(mine + (long long)q * cap + i);
     data[i] = s;
   }
+  // (every thread read the counter before the first barrier above)
+  if (epoch_ctr != nullptr && threadIdx.x == 0) *epoch_ctr = epoch;
 }
 
 }  // namespace cc
 
 extern "C" int cc_peer_allreduce(float* data, int32_t n, int32_t world, int32_t rank,
                                  float* const* slots, uint32_t* const* flags, int64_t cap,
-                                 uint32_t epoch, cc_stream_t stream) {
+                                 uint32_t epoch, uint32_t* epoch_ctr, cc_stream_t stream) {
   CC_REQUIRE(world >= 1 && world <= CC_PEER_MAX && rank >= 0 && rank < world,
              "cc_peer_allreduce: world=%d rank=%d", world, rank);
   CC_REQUIRE(n >= 0 && n <= cap, "cc_peer_allreduce: n=%d exceeds the slot capacity %lld", n,
@@ -253,7 +269,7 @@ extern "C" int cc_peer_allreduce(float* data, int32_t n, int32_t world, int32_t 
   }
   const int threads = n >= 1024 ? 1024 : ((n + 31) / 32 * 32 < 32 ? 32 : (n + 31) / 32 * 32);
   peer_allreduce_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(ap, world, rank, data, n, cap,
-                                                                  epoch);
+                                                                  epoch, epoch_ctr);
   CC_CHECK_LAUNCH();
   return 0;
 }

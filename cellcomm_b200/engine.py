@@ -268,7 +268,10 @@ class TorchDist:
                 a = self.symmetric_zeros(2 * W * self._AR_CAP, torch.float32, device)
                 if a is not None:
                     b = self.symmetric_zeros(W, torch.int32, device)
-                    st = {"slots": a[1], "flags": b[1], "keep": (a, b), "epoch": 0}
+                    # epoch counter on the device (advanced by the kernel itself): the call
+                    # is identical every time, so a captured CUDA graph can replay it
+                    st = {"slots": a[1], "flags": b[1], "keep": (a, b),
+                          "ctr": torch.zeros(1, dtype=torch.int32, device=device)}
             self._ar = st
         return st or None
 
@@ -280,9 +283,8 @@ class TorchDist:
                     t.numel() <= self._AR_CAP:
                 st = self._peer_allreduce_state(t.device)
             if st is not None:
-                st["epoch"] += 1
                 ops.peer_allreduce(t, self.world_size, self.rank, st["slots"], st["flags"],
-                                   self._AR_CAP, st["epoch"])
+                                   self._AR_CAP, 1, epoch_ctr=st["ctr"])
             else:
                 self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
@@ -412,8 +414,10 @@ class Net:
                     mc = int(h2.multicast_ptr or 0)     # NVSwitch multimem mapping (0: none)
                 except Exception:
                     mc = 0
+            # update counter on the device: every hand-shake of update u uses epoch ctr + 1 and
+            # the update's last kernel advances ctr, so the step is CUDA-graph capturable
             self.peer = {"stage": s_ptrs, "p16": w_ptrs, "p16_mc": mc, "handles": [h1, h2],
-                         "epoch": 0}
+                         "ctr": torch.zeros(1, dtype=torch.int32, device=dev)}
         else:
             self.g32 = torch.zeros_like(self.p32)
             self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
@@ -817,8 +821,7 @@ class Net:
         if train and self._bucketed():
             for bk in self.buckets:
                 bk["pending"], bk["launched"] = bk["pieces"], False
-            if self.peer is not None:
-                self.peer["epoch"] += 1
+
         out_t = g.output
         seed = self._buf(self.grad, out_t)[:rows]
         if g.widths[out_t] > 0 and dout.data_ptr() != seed.data_ptr():
@@ -1034,15 +1037,15 @@ class Net:
         """signal "my gradient of this bucket is complete" -> fused peer-memory optimiser kernel
         -> signal "consumed / my shard is written" (csrc/peer_optimizer.cu)."""
         pr, W, r = self.peer, self.dist.world_size, self.dist.rank
-        ops.peer_signal([self._flag_ptr(t, 0, bucket, r) for t in range(W)], pr["epoch"])
+        ops.peer_signal([self._flag_ptr(t, 0, bucket, r) for t in range(W)], 1, epoch_ctr=pr["ctr"])
         if broadcast:   # sharded bucket: all contributions were pushed into MY staging slots
             grads = [pr["stage"][r] + 4 * q * self.n_flat for q in range(W)]
         else:           # replicated tail: pull every rank's own (small) gradient
             grads = [pr["stage"][q] + 4 * q * self.n_flat for q in range(W)]
         ops.peer_rmsprop(W, r, grads, pr["p16"], self.p32, self.ms, self.mom, start, count,
                          broadcast, LR, RHO, MOMENTUM, EPSILON, self._flag_ptr(r, 0, bucket, 0),
-                         pr["epoch"], p16_multicast=pr["p16_mc"])
-        ops.peer_signal([self._flag_ptr(t, 1, bucket, r) for t in range(W)], pr["epoch"])
+                         1, p16_multicast=pr["p16_mc"], epoch_ctr=pr["ctr"])
+        ops.peer_signal([self._flag_ptr(t, 1, bucket, r) for t in range(W)], 1, epoch_ctr=pr["ctr"])
 
     def _reduce_and_update(self):
         """Data-parallel update.  world == 1: one sweep.  world > 1 (ZeRO-1 style): reduce-scatter
@@ -1065,7 +1068,7 @@ class Net:
                 pr = self.peer
                 self._peer_update(pr["nb"] - 1, K, self.n_flat - K, broadcast=False)
                 ops.peer_wait(self._flag_ptr(self.dist.rank, 1, 0, 0),
-                              pr["nb"] * self.dist.world_size, pr["epoch"])
+                              pr["nb"] * self.dist.world_size, 1, epoch_ctr=pr["ctr"], bump=True)
                 self._master_stale = True
                 return
             tail = slice(K, self.n_flat)
@@ -1182,9 +1185,12 @@ class GraphedStep:
         self.idx = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.x16 = ops.alloc2d(batch, n_cols, device=dev)
         saved = [(n, n.opt_stream) for n in eng.nets.values()]
-        for n, _ in saved:                       # no side streams inside the capture
+        for n, _ in saved:
             n._wait_optimizer()
-            n.opt_stream = None
+            if eng.dist.world_size == 1:         # single GPU: nothing runs on the side stream
+                n.opt_stream = None
+        # data parallel (peer-memory path): the gradient exchange / update kernels stay on the
+        # optimiser stream; it forks from and joins the capturing stream inside the graph
 
         def body():
             ops.gather_rows(rowptr, colidx, values, n_cols, row_idx=self.idx, out16=self.x16)
@@ -1193,7 +1199,9 @@ class GraphedStep:
             else:
                 ops.cast_f32_to_bf16(eng.z32[:batch], eng.z16[:batch])
                 ops.cast_f32_to_bf16(eng.r32[:batch], eng.r16[:batch])
-            return eng.train_step(self.x16)
+            out = eng.train_step(self.x16)
+            eng.join()                           # side-stream work joins before the capture ends
+            return out
 
         try:
             # warm-up run (allocates lazy buffers, sets kernel attributes, fills the tensor-map
@@ -1508,6 +1516,18 @@ class BiGanEngine:
         self.last_losses = Lc
         return g, e, d
 
+    def peer_graphable(self):
+        """Data-parallel step without any NCCL call inside (gradient exchange, optimiser and the
+        small all-reduces all run as peer-memory kernels with device-resident epochs), so
+        capture_step() may record it.  CELLCOMM_B200_DP_GRAPH=0 keeps data parallel eager."""
+        if self.dist.world_size == 1:
+            return True
+        if os.environ.get("CELLCOMM_B200_DP_GRAPH", "1") == "0":
+            return False
+        probe = getattr(self.dist, "_peer_allreduce_state", None)
+        return (all(n.peer is not None for n in self.nets.values()) and probe is not None
+                and probe(self.device) is not None)
+
     # ------------------------------------------------------------------ CUDA graph of a step
     def capture_step(self, csr, n_cols, batch, latents="device"):
         """Capture gather -> (priors) -> trainings_step for a fixed batch size into ONE CUDA
@@ -1520,8 +1540,9 @@ class BiGanEngine:
         index buffer to fill before .replay()."""
         if self.device.type != "cuda":
             raise RuntimeError("CUDA graphs need a CUDA device")
-        if self.dist.world_size > 1:
-            raise RuntimeError("graph capture is single-GPU (collectives are not captured)")
+        if self.dist.world_size > 1 and not self.peer_graphable():
+            raise RuntimeError("graph capture needs the peer-memory data-parallel path (NCCL "
+                               "collectives are not captured)")
         self.reserve(batch)
         key = (int(batch), latents, csr[0].data_ptr(), csr[1].data_ptr(), csr[2].data_ptr())
         gs = self._graphs.get(key)

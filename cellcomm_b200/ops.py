@@ -381,7 +381,7 @@ def fill_f32(t, value):
 
 # --------------------------------------------------------------------------- peer-memory optimiser
 def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, broadcast, lr, rho,
-                 momentum, eps, ready_ptr, epoch, p16_multicast=0):
+                 momentum, eps, ready_ptr, epoch, p16_multicast=0, epoch_ctr=None):
     """Fused reduce-scatter -> Keras RMSprop -> bf16 all-gather over NVLink peer memory for the
     flat element range [start, start+count).  grad_ptrs / p16_ptrs: device pointers (ints) of
     every rank's flat gradient / bf16 weight buffer; p32, ms, mom: this rank's flat buffers."""
@@ -396,26 +396,32 @@ def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, b
     d.lr, d.rho, d.momentum, d.eps = float(lr), float(rho), float(momentum), float(eps)
     d.ready, d.epoch = int(ready_ptr), int(epoch) & 0xFFFFFFFF
     d.p16_multicast = int(p16_multicast) or None
+    d.epoch_ctr = _p(epoch_ctr)
     check(_lib.load().cc_peer_rmsprop(C.byref(d), _stream()))
 
 
-def peer_signal(target_ptrs, value):
-    """After everything this stream has done so far, store `value` to every flag address."""
+def peer_signal(target_ptrs, value, epoch_ctr=None):
+    """After everything this stream has done so far, store `value` (+ *epoch_ctr) to every flag."""
     arr = (C.c_void_p * len(target_ptrs))(*[int(p) for p in target_ptrs])
-    check(_lib.load().cc_peer_signal(arr, len(target_ptrs), int(value) & 0xFFFFFFFF, _stream()))
+    check(_lib.load().cc_peer_signal(arr, len(target_ptrs), int(value) & 0xFFFFFFFF,
+                                     _p(epoch_ctr), _stream()))
 
 
-def peer_wait(flags_ptr, n, value):
-    """Block the stream until n consecutive local uint32 flags are >= value."""
-    check(_lib.load().cc_peer_wait(int(flags_ptr), int(n), int(value) & 0xFFFFFFFF, _stream()))
+def peer_wait(flags_ptr, n, value, epoch_ctr=None, bump=False):
+    """Block the stream until n consecutive local uint32 flags are >= value (+ *epoch_ctr);
+    bump: then advance the counter to that epoch."""
+    check(_lib.load().cc_peer_wait(int(flags_ptr), int(n), int(value) & 0xFFFFFFFF, _p(epoch_ctr),
+                                   int(bool(bump)), _stream()))
 
 
-def peer_allreduce(data, world, rank, slot_ptrs, flag_ptrs, cap, epoch):
-    """In-place sum all-reduce of a small contiguous fp32 tensor over peer memory (one kernel)."""
+def peer_allreduce(data, world, rank, slot_ptrs, flag_ptrs, cap, epoch, epoch_ctr=None):
+    """In-place sum all-reduce of a small contiguous fp32 tensor over peer memory (one kernel);
+    with epoch_ctr the kernel uses epoch + *epoch_ctr and leaves that value in the counter."""
     _req(data, torch.float32, "data")
     if not data.is_contiguous():
         raise ValueError("peer_allreduce: data must be contiguous")
     sl = (C.c_void_p * world)(*[int(p) for p in slot_ptrs])
     fl = (C.c_void_p * world)(*[int(p) for p in flag_ptrs])
     check(_lib.load().cc_peer_allreduce(data.data_ptr(), data.numel(), int(world), int(rank), sl, fl,
-                                        int(cap), int(epoch) & 0xFFFFFFFF, _stream()))
+                                        int(cap), int(epoch) & 0xFFFFFFFF, _p(epoch_ctr),
+                                        _stream()))

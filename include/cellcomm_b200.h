@@ -325,7 +325,8 @@ int cc_rmsprop_step(float* p32, void* p16, const float* g, float* ms, float* mom
  *                     staging slots, already filled by every rank's wgrad GEMM epilogues
  * cc_peer_signal stores `value` to n remote/local flags after a system-scope fence (everything
  * the stream did before is visible to the peers first); cc_peer_wait blocks the stream until
- * n consecutive local flags are >= value.  Epochs are compared modulo 2^32. */
+ * n consecutive local flags are >= value.  Epochs are compared modulo 2^32; every entry point
+ * accepts a device counter `epoch_ctr` that is added to the host-side value (NULL: none). */
 #define CC_PEER_MAX 16
 typedef struct cc_peer_rmsprop_desc {
   int32_t world, rank;
@@ -339,6 +340,11 @@ typedef struct cc_peer_rmsprop_desc {
   float lr, rho, momentum, eps;
   const uint32_t* ready;
   uint32_t epoch;
+  /* optional device-resident epoch base: effective epoch = epoch + *epoch_ctr.  With it the
+   * whole step (hand-shakes included) can be captured in a CUDA graph: every replay sees the
+   * counter the previous update left behind (cc_peer_wait(bump = 1) / cc_peer_allreduce
+   * advance it). NULL: epoch is the host's value. */
+  const uint32_t* epoch_ctr;
   /* optional NVLS multicast address of the bf16 weight buffer (NVSwitch multimem mapping of
    * the same symmetric allocation): with broadcast = 1 ONE multimem.st per 16 bytes delivers
    * the updated weights to every rank, instead of world P2P stores (7/8 less NVLink egress
@@ -346,14 +352,17 @@ typedef struct cc_peer_rmsprop_desc {
   void* p16_multicast;
 } cc_peer_rmsprop_desc;
 int cc_peer_rmsprop(const cc_peer_rmsprop_desc* desc, cc_stream_t stream);
-int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value, cc_stream_t stream);
-int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, cc_stream_t stream);
+int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value,
+                   const uint32_t* epoch_ctr, cc_stream_t stream);
+int cc_peer_wait(const uint32_t* flags, int32_t n, uint32_t value, uint32_t* epoch_ctr,
+                 int32_t bump, cc_stream_t stream);
 /* In-place sum all-reduce of n <= cap floats over peer memory in one kernel (BatchNorm batch
  * statistics, BN-backward sums, loss buffer).  slots[q]: rank q's [2][world][cap] staging array,
  * flags[q]: rank q's [world] flags (both peer-mapped); epoch grows by one per call, identically
  * on every rank.  Sums in rank order, so every rank gets bit-identical results. */
 int cc_peer_allreduce(float* data, int32_t n, int32_t world, int32_t rank, float* const* slots,
-                      uint32_t* const* flags, int64_t cap, uint32_t epoch, cc_stream_t stream);
+                      uint32_t* const* flags, int64_t cap, uint32_t epoch, uint32_t* epoch_ctr,
+                      cc_stream_t stream);
 
 /* Dense layer with zero input width: y[r,c] = act(bias[c]).  The reference's 5-gene fixture
  * produces Dense(0) layers (int(5*0.1) == 0; src/bigan_cont.py:8,29) whose consumers see K=0. */

@@ -26,6 +26,20 @@ for step in range(3):
     e.set_latents(torch.rand(B, 3, generator=g), torch.rand(B, 3, generator=g), B)
     losses = [float(v) for v in e.train_step(x16)]
     assert all(np.isfinite(losses)), losses
+# the same step as ONE CUDA graph per rank (gather + priors + eight sub-steps + peer-memory
+# gradient exchange / optimiser / all-reduces with device-resident epochs), replayed twice
+graph_mode = "eager only"
+if e.peer_graphable():
+    from cellcomm_b200.cell_type_training import CellMatrix
+    dense = ((torch.rand(4 * B, G, generator=g) < 0.06).float() *
+             (torch.poisson(torch.full((4 * B, G), 1.2), generator=g) + 1)).numpy().astype(np.float64)
+    csr = CellMatrix.from_dense(dense).device_csr("cuda")
+    gs = e.capture_step(csr, G, B, latents="device")
+    for step in range(2):
+        idx = torch.from_numpy(np.random.RandomState(rank * 10 + step).permutation(4 * B)[:B])
+        losses = [float(v) for v in gs.replay(idx)]
+        assert all(np.isfinite(losses)), losses
+    graph_mode = f"+ 2 CUDA-graph replays ({gs.launches_per_replay} kernels each)"
 e.join()
 torch.cuda.synchronize()
 for name, n in e.nets.items():
@@ -47,5 +61,5 @@ if rank == 0:
     mode = "NCCL reduce-scatter / all-gather" if pr is None else (
         "peer-memory push + fused optimiser, all-gather by " +
         ("NVLS multicast stores" if pr["p16_mc"] else "P2P stores"))
-    print(f"dp_check ok: world={world} losses={losses} [{mode}]")
+    print(f"dp_check ok: world={world} losses={losses} [{mode}] [{graph_mode}]")
 dist.destroy_process_group()

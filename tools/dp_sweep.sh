@@ -24,6 +24,8 @@ for label in "$@"; do
     skip_update) run skip_update CELLCOMM_B200_DP_SKIP_UPDATE=1 ;;
     nccl) run nccl CELLCOMM_B200_PEER_OPT=0 ;;
     sync) run sync CELLCOMM_B200_ASYNC_OPT=0 ;;
+    graph) run graph A=1 ;;
+    eager) run eager CELLCOMM_B200_DP_GRAPH=0 ;;
     nccl_allreduce) run nccl_allreduce CELLCOMM_B200_PEER_ALLREDUCE=0 ;;
   esac
 done
