@@ -349,6 +349,28 @@ def run_ours(args):
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
     clock_info = clocks.stop() if rank == 0 else None
 
+    # ---- the same call fed the way the reference feeds it: a dense float32 host batch (the
+    # DataFrame.sample() rows, src/cell_type_training.py:37-38), 276 MB host->device per step
+    dense_e2e = None
+    if world == 1 and args.dense_e2e_steps > 0:
+        xb = torch.empty((B, args.genes), dtype=torch.float32).pin_memory()
+        xb.copy_(torch.from_numpy(trainer.sample_cell_data().to_numpy(np.float32)))
+        xnp = xb.numpy()
+        [float(v) for v in net.trainings_step(xnp)]
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.dense_e2e_steps):
+            g, el, d = net.trainings_step(xnp)
+            _ = (float(g), float(el), float(d))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_dense = ev0.elapsed_time(ev1) / args.dense_e2e_steps
+        dense_e2e = {"value": B / (ms_dense / 1e3), "unit": "cells/s", "ms_per_step": ms_dense,
+                     "h2d_bytes_per_step": B * args.genes * 4 + 2 * B * Z * 4,
+                     "d2h_bytes_per_step": 12, "steps": args.dense_e2e_steps,
+                     "path": "network.trainings_step(float32 ndarray [B, genes]) from pinned host "
+                             "memory: H2D copy of the dense batch + cast, eager step, losses read back"}
+
     if args.no_roofline:          # quick sweeps: the two train numbers only
         if rank == 0:
             print(json.dumps({
@@ -509,6 +531,7 @@ def run_ours(args):
                 "path": "CellTraining.sample_cell_data() + network.trainings_step(batch): host "
                         "numpy sampling, pageable->device copy of the batch indices and priors, "
                         "three loss floats read back per step"},
+        "e2e_dense_host_batch": dense_e2e,
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "tensor",
@@ -738,6 +761,8 @@ def main():
                          "headline); classify: ClassifyCellBiGan (configs[3]); encode: the "
                          "encode-only pass over --encode-cells cells (configs[4])")
     ap.add_argument("--encode-cells", type=int, default=1_000_000)
+    ap.add_argument("--dense-e2e-steps", type=int, default=3,
+                    help="steps of the dense-host-batch end-to-end variant (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true",
                     help="train numbers only (tuning sweeps); the driver's runs never pass this")

@@ -121,3 +121,39 @@ def test_loss_scalar_behaves_like_a_float():
     assert float(acc) == 3.0
     assert f"{acc:6.3f}" == " 3.000"
     assert float(sum((a, a, a))) == 4.5
+
+
+@pytest.mark.parametrize("bucket_elems", [1 << 11, 1 << 14, 1 << 30])
+def test_gradient_buckets_tile_the_kernel_region(monkeypatch, bucket_elems):
+    """Data-parallel gradient buckets (engine.Net._build_buckets): the row pieces of every
+    Dense kernel are disjoint, 64-element aligned (so 1/world shards of 2, 4 or 8 ranks stay
+    16-byte aligned), cover every kernel element, respect Concatenate segment boundaries, and
+    consecutive pieces group into contiguous buckets."""
+    monkeypatch.setattr(eng, "_BUCKET_ELEMS", bucket_elems)
+    e = eng.BiGanEngine("cont", 3, 700, max_batch=4, device="cpu", seed=0)
+    for net in e.nets.values():
+        covered = torch.zeros(net.small_off, dtype=torch.int32)
+        for (layer, seg), pieces in net.pieces.items():
+            L = net.layers[layer]
+            seg_lo = sum(L["in_widths"][:seg])
+            seg_hi = seg_lo + L["in_widths"][seg]
+            assert pieces[0]["lo"] == seg_lo and pieces[-1]["hi"] == seg_hi
+            for a, b in zip(pieces, pieces[1:]):
+                assert a["hi"] == b["lo"] and (b["lo"] - seg_lo) % 64 == 0
+            for pc in pieces:
+                assert pc["start"] == L["w_off"] + pc["lo"] * L["ld"]
+                assert pc["start"] % 64 == 0 and pc["end"] % 64 == 0
+                assert pc["end"] >= L["w_off"] + pc["hi"] * L["ld"]
+                covered[pc["start"]:pc["end"]] += 1
+                bk = pc["bucket"]
+                assert bk["start"] <= pc["start"] and pc["end"] <= bk["end"]
+        assert int(covered.max()) <= 1
+        for L in net.layers:
+            if L["kind"] == "dense" and L["K"] * L["N"] > 0:
+                assert bool((covered[L["w_off"]:L["w_off"] + L["K"] * L["ld"]] == 1).all())
+        for a, b in zip(net.buckets, net.buckets[1:]):
+            assert a["end"] <= b["start"]
+        for bk in net.buckets:
+            assert (bk["end"] - bk["start"]) % 64 == 0 and bk["pieces"] >= 1
+        if bucket_elems == 1 << 11:
+            assert max(len(p) for p in net.pieces.values()) >= 2     # big kernels were cut
