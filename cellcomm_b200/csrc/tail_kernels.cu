@@ -305,10 +305,34 @@ __device__ __forceinline__ void load_pair(const Mat& m, long long r, long long c
   }
 }
 
+__device__ __forceinline__ void store_pair(const Mat& m, long long r, long long c, bool c0ok,
+                                           bool c1ok, float x0, float x1) {
+  if (m.f32) {
+    float* p = reinterpret_cast<float*>(m.p) + r * m.ld + c;
+    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
+      *reinterpret_cast<float2*>(p) = make_float2(x0, x1);
+    } else {
+      if (c0ok) p[0] = x0;
+      if (c1ok) p[1] = x1;
+    }
+  } else {
+    bf16* p = reinterpret_cast<bf16*>(m.p) + r * m.ld + c;
+    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 3) == 0)) {
+      *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x0, x1);
+    } else {
+      if (c0ok) p[0] = f2bf(x0);
+      if (c1ok) p[1] = f2bf(x1);
+    }
+  }
+}
+
+// MODE 3 optionally also WRITES dz = dy*act'(y) (the wgrad / dgrad GEMM operand), so a trained
+// Dense layer needs one pass over dy and y instead of act_bwd + bias_grad
 template <int MODE>  // 0: x (1 output)  1: x, x^2   2: dy, dy*xhat   3: dy*act'(y) (1 output)
 __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long long cols,
                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                 float* __restrict__ out, int accumulate, int act) {
+                                 float* __restrict__ out, int accumulate, int act,
+                                 const Mat dz = Mat{nullptr, 0, 0}) {
   __shared__ float s0[8][64], s1[8][64];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long c = (long long)blockIdx.x * 64 + tx * 2;
@@ -344,8 +368,11 @@ __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long 
       } else {
         float y0 = 0.f, y1 = 0.f;
         if (act != 0) load_pair(b, r, c, c0ok, c1ok, y0, y1);
-        a0 += x0 * (act == CC_ACT_SIGMOID ? y0 * (1.f - y0) : (act == CC_ACT_RELU ? (y0 > 0.f ? 1.f : 0.f) : 1.f));
-        a1 += x1 * (act == CC_ACT_SIGMOID ? y1 * (1.f - y1) : (act == CC_ACT_RELU ? (y1 > 0.f ? 1.f : 0.f) : 1.f));
+        const float v0 = x0 * (act == CC_ACT_SIGMOID ? y0 * (1.f - y0) : (act == CC_ACT_RELU ? (y0 > 0.f ? 1.f : 0.f) : 1.f));
+        const float v1 = x1 * (act == CC_ACT_SIGMOID ? y1 * (1.f - y1) : (act == CC_ACT_RELU ? (y1 > 0.f ? 1.f : 0.f) : 1.f));
+        a0 += v0;
+        a1 += v1;
+        if (dz.p != nullptr) store_pair(dz, r, c, c0ok, c1ok, v0, v1);
       }
     }
   }
@@ -380,7 +407,7 @@ __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long 
 template <int MODE>
 static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long long cols,
                             const float* mean, const float* rstd, float* out, int accumulate,
-                            cudaStream_t st, int act = 0) {
+                            cudaStream_t st, int act = 0, const Mat dz = Mat{nullptr, 0, 0}) {
   const unsigned gx = (unsigned)((cols + 63) / 64);
   // enough row slabs to cover ~2 waves of the machine when there are few column blocks
   unsigned gy = 1;
@@ -397,7 +424,7 @@ static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long lon
     CC_CHECK_LAUNCH();
   }
   colreduce_kernel<MODE><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(a, b, rows, cols, mean, rstd, out,
-                                                               accumulate, act);
+                                                               accumulate, act, dz);
   CC_CHECK_LAUNCH();
   return 0;
 }
@@ -699,8 +726,8 @@ extern "C" int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, 
 }
 
 extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
-                            int64_t cols, int32_t act, float* out, int32_t dtypes,
-                            cc_stream_t stream) {
+                            int64_t cols, int32_t act, float* out, void* dz, int64_t lddz,
+                            int32_t dtypes, cc_stream_t stream) {
   if (cols <= 0) return 0;
   if (rows <= 0) {
     fill_f32_kernel<<<ew_grid(cols, 256), 256, 0, ST(stream)>>>(out, 0.f, cols);
@@ -708,7 +735,8 @@ extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t
     return 0;
   }
   return launch_colreduce<3>(mat(dy, lddy, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), rows, cols,
-                             nullptr, nullptr, out, 0, ST(stream), act);
+                             nullptr, nullptr, out, 0, ST(stream), act,
+                             mat(dz, lddz, F32(dtypes, 2)));
 }
 
 extern "C" int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo,

@@ -249,8 +249,9 @@ class TorchDist:
         except Exception as exc:      # fails on every rank alike: fall back to the NCCL path
             self._symm_failed = True
             if self.rank == 0:
+                import sys
                 print(f"cellcomm_b200: symmetric memory unavailable ({exc}); data-parallel "
-                      f"updates use NCCL reduce-scatter / all-gather", flush=True)
+                      f"updates use NCCL reduce-scatter / all-gather", file=sys.stderr, flush=True)
             return None
         assert ptrs[self.rank] == t.data_ptr(), "symmetric memory: local pointer mismatch"
         return t, ptrs, hdl
@@ -849,6 +850,10 @@ class Net:
                     dz_lo = self._buf(self.split_lo, ("dz", out))[:rows]
                     ops.split_bf16(dy, dz, dz_lo)
                     dzs = [dz, dz_lo]
+                elif train:
+                    # one pass over dy and y: dz for the GEMMs and the bias gradient
+                    ops.bias_grad(dy, A[out], act, L["db"], dz=dz)
+                    dzs = [dz]
                 else:
                     ops.act_bwd(dy, A[out], dz, act)
                     dzs = [dz]
@@ -892,8 +897,7 @@ class Net:
                 if train:
                     if out in self.prebn:
                         ops.bias_grad(dy, A[out], 0, L["db"])     # dy already holds dz (fp32)
-                    else:
-                        ops.bias_grad(dy, A[out], act, L["db"])
+                    # (other layers: done together with dz above)
             elif kind == "softmax":
                 i = node["ins"][0]
                 if width > 0 and needs[i]:

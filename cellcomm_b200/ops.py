@@ -215,11 +215,13 @@ def colsum(x, out32, beta=0):
                                 _mask(x), _stream()))
 
 
-def bias_grad(dy, y, act, out32):
-    """out32[c] = sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient)."""
+def bias_grad(dy, y, act, out32, dz=None):
+    """out32[c] = sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient);
+    dz (optional): also store dy * act'(y) there (one pass instead of act_bwd + bias_grad)."""
     _req(out32, torch.float32, "out")
     check(_lib.load().cc_bias_grad(_p(dy), _ld(dy), _p(y), _ld(y), dy.shape[0], dy.shape[1],
-                                   int(act), _p(out32), _mask(dy, y), _stream()))
+                                   int(act), _p(out32), _p(dz), _ld(dz), _mask(dy, y, dz),
+                                   _stream()))
 
 
 def split_bf16(x, hi, lo):

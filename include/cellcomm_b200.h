@@ -195,9 +195,12 @@ int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
 
 /* Dense bias gradient from the fp32 upstream gradient: out[c] = sum_r dy[r,c]*act'(y[r,c]).
  * (Summing the bf16 dZ instead loses the near-cancelling sums of biases that feed a
- * BatchNormalization.)  dtypes: dy, y */
+ * BatchNormalization.)  dz (optional, NULL to skip): also write dz[r,c] = dy*act'(y), the
+ * operand of the wgrad / dgrad GEMMs, in the same pass (replaces a cc_act_bwd launch for
+ * trained layers).  dtypes: dy, y, dz */
 int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
-                 int64_t cols, int32_t act, float* out, int32_t dtypes, cc_stream_t stream);
+                 int64_t cols, int32_t act, float* out, void* dz, int64_t lddz, int32_t dtypes,
+                 cc_stream_t stream);
 /* hi = bf16(x), lo = bf16(x - hi): two-term bf16 expansion of an activation, fed to cc_gemm
  * as two accumulating segments where 8 mantissa bits are too few.  dtypes: x */
 int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo, int64_t ldlo,
