@@ -741,6 +741,69 @@ def run_reference_encode(args):
                 "d2h_bytes_per_step": 0}}), flush=True)
 
 
+# ------------------------------------------------------------------------------ loader
+def write_synthetic_mtx(path, n_cells, n_genes, seed):
+    """10x-shaped MatrixMarket text (3 header lines, `gene barcode count`, barcode-major,
+    genes ascending inside a barcode): ~2,000 non-zeros per cell.  Host only."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    nnz_row = np.clip(np.round(rng.lognormal(np.log(2000.0), 0.35, n_cells)), 200,
+                      min(8000, n_genes)).astype(np.int64)
+    rows = []
+    for c in range(n_cells):
+        g = np.sort(rng.choice(n_genes, nnz_row[c], replace=False)) + 1
+        v = 1 + rng.geometric(0.45, nnz_row[c])
+        rows.append(np.stack([g, np.full_like(g, c + 1), v], 1))
+    coo = np.concatenate(rows)
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate integer general\n%\n")
+        f.write(f"{n_genes} {n_cells} {len(coo)}\n")
+        np.savetxt(f, coo, fmt="%d %d %d")
+    return len(coo)
+
+
+def run_loader(args):
+    """`load_matrix` (src/cell_type_training.py:9-17) on a synthetic 10x
+    .mtx: the C++ parser + compact-index CSR builder behind the C ABI (cc_mtx_load_csr) against
+    the reference's own pandas body (oracle/loader_oracle.load_matrix_pandas) on the same file,
+    results compared (bit-exact).  Host code: no GPU involved, no roofline."""
+    import tempfile
+    import numpy as np
+    from cellcomm_b200.cell_type_training import load_matrix
+    from oracle import loader_oracle as LO
+    n_cells = args.loader_cells
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "matrix.mtx")
+        nnz = write_synthetic_mtx(path, n_cells, args.genes, 20260103)
+        size = os.path.getsize(path)
+        load_matrix(path)
+        times = []
+        for _ in range(max(1, args.steps)):
+            t0 = time.perf_counter()
+            m = load_matrix(path)
+            times.append(time.perf_counter() - t0)
+        t_ours = min(times)
+        t0 = time.perf_counter()
+        ref = LO.load_matrix_pandas(path)
+        t_ref = time.perf_counter() - t0
+        same = (m.shape == ref.shape and
+                np.array_equal(m.dense_rows(np.arange(min(64, n_cells))),
+                               ref.values[:min(64, n_cells)].astype(np.float64)))
+    print(json.dumps({
+        "metric": "load_matrix nnz/sec", "value": nnz / t_ours, "unit": "nnz/s", "n_gpus": 0,
+        "steps": args.steps, "warmup": 1, "ms_per_step": t_ours * 1e3, "higher_is_better": True,
+        "scaling": "n/a", "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+        "config": {"workload": f"load_matrix on a synthetic 10x .mtx, {n_cells} cells x "
+                               f"{args.genes} genes, {nnz} non-zeros, {size / 1e6:.0f} MB of text",
+                   "cells": n_cells, "genes": args.genes},
+        "file_MB_per_s": size / t_ours / 1e6, "matches_reference_pandas_body": bool(same),
+        "cpu_baseline": {"value": nnz / t_ref, "unit": "nnz/s", "cores": 1, "kind": "reference",
+                         "sample": "the reference's pandas read_csv + pivot_table body on the same "
+                                   "file (oracle/loader_oracle.load_matrix_pandas), one pass",
+                         "seconds": t_ref},
+        "roofline": None, "gpu_launches": 0}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -756,10 +819,12 @@ def main():
     ap.add_argument("--genes", type=int, default=GENES)
     ap.add_argument("--encode-tile", type=int, default=4096)
     ap.add_argument("--encode-reps", type=int, default=2)
-    ap.add_argument("--workload", default="train", choices=["train", "classify", "encode"],
+    ap.add_argument("--loader-cells", type=int, default=2000)
+    ap.add_argument("--workload", default="train", choices=["train", "classify", "encode", "loader"],
                     help="train: ContinuousCellBiGan trainings_step (BASELINE configs[1], the "
                          "headline); classify: ClassifyCellBiGan (configs[3]); encode: the "
-                         "encode-only pass over --encode-cells cells (configs[4])")
+                         "encode-only pass over --encode-cells cells (configs[4]); loader: "
+                         "load_matrix on a synthetic .mtx (host C++ vs the reference's pandas)")
     ap.add_argument("--encode-cells", type=int, default=1_000_000)
     ap.add_argument("--dense-e2e-steps", type=int, default=3,
                     help="steps of the dense-host-batch end-to-end variant (0: skip)")
@@ -770,7 +835,9 @@ def main():
                     help="1: run the device-resident loop as one CUDA graph per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "loader":
+        run_loader(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "encode":
         run_encode(args)

@@ -20,7 +20,10 @@
 #include <cerrno>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <memory>
+#include <ctime>
 #include <string>
 #include <thread>
 #include <vector>
@@ -42,10 +45,24 @@ struct cc_csr {
 
 namespace {
 
-struct Triplets {
-  std::vector<int64_t> gene, barcode;
-  std::vector<double> val;
+// CC_LOADER_TIMING=1: stage timings on stderr
+struct StageTimer {
+  bool on;
+  double t0;
+  static double now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  StageTimer() : on(getenv("CC_LOADER_TIMING") != nullptr), t0(now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "cc loader: %-28s %8.1f ms\n", what, (t - t0) * 1e3);
+    t0 = t;
+  }
 };
+
 
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r'; }
 
@@ -91,8 +108,11 @@ inline bool parse_number(const char*& p, const char* end, double* out, bool* is_
   return true;
 }
 
-// parse lines in [p, end); returns false (with line text) on a malformed line
-bool parse_chunk(const char* p, const char* end, Triplets* out, std::string* err) {
+// parse lines in [p, end) into the caller's slices (capacity >= number of newlines + 1);
+// returns the number of entries, or -1 (with the line text) on a malformed line
+int64_t parse_chunk(const char* p, const char* end, int64_t* gene, int64_t* barcode, double* val,
+                    std::string* err) {
+  int64_t n = 0;
   while (p < end) {
     // skip blank lines (pandas skip_blank_lines=True)
     const char* ls = p;
@@ -115,14 +135,47 @@ bool parse_chunk(const char* p, const char* end, Triplets* out, std::string* err
       const char* le = ls;
       while (le < end && *le != '\n') ++le;
       *err = std::string(ls, std::min<size_t>((size_t)(le - ls), 80));
-      return false;
+      return -1;
     }
-    out->gene.push_back(giv);
-    out->barcode.push_back(biv);
-    out->val.push_back(v);
+    gene[n] = giv;
+    barcode[n] = biv;
+    val[n] = v;
+    ++n;
     if (p < end) ++p;  // newline
   }
-  return true;
+  return n;
+}
+
+inline int64_t count_newlines(const char* p, const char* end) {
+  int64_t n = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    if (!nl) break;
+    ++n;
+    p = nl + 1;
+  }
+  return n;
+}
+
+template <typename F>
+void parallel_ranges(int64_t n, unsigned nt, F f) {
+  if (nt <= 1 || n < 2) {
+    f(0, n, 0u);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    th.emplace_back([=] { f(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+unsigned worker_threads() {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 32) nt = 32;
+  return nt;
 }
 
 // ids -> (sorted distinct ids, compact index of every element)
@@ -138,15 +191,21 @@ void compact_ids(const int64_t* ids, int64_t n, std::vector<int64_t>* distinct,
   }
   const int64_t range = hi - lo + 1;
   if (range <= std::max<int64_t>(4 * n, 1 << 20)) {
+    const unsigned nt = n > (1 << 18) ? worker_threads() : 1;
     std::vector<int32_t> lut((size_t)range, -1);
-    for (int64_t i = 0; i < n; ++i) lut[(size_t)(ids[i] - lo)] = 0;
+    // (threads may mark the same id: every writer stores the same value)
+    parallel_ranges(n, nt, [&](int64_t a, int64_t b, unsigned) {
+      for (int64_t i = a; i < b; ++i) lut[(size_t)(ids[i] - lo)] = 0;
+    });
     int32_t next = 0;
     for (int64_t k = 0; k < range; ++k)
       if (lut[(size_t)k] == 0) {
         lut[(size_t)k] = next++;
         distinct->push_back(lo + k);
       }
-    for (int64_t i = 0; i < n; ++i) (*index)[(size_t)i] = lut[(size_t)(ids[i] - lo)];
+    parallel_ranges(n, nt, [&](int64_t a, int64_t b, unsigned) {
+      for (int64_t i = a; i < b; ++i) (*index)[(size_t)i] = lut[(size_t)(ids[i] - lo)];
+    });
   } else {
     std::vector<int64_t> s(ids, ids + n);
     std::sort(s.begin(), s.end());
@@ -161,50 +220,95 @@ void compact_ids(const int64_t* ids, int64_t n, std::vector<int64_t>* distinct,
 int build_csr(const int64_t* gene, const int64_t* barcode, const double* val, int64_t nnz,
               cc_csr** out) {
   cc_csr* c = new cc_csr();
+  StageTimer tm;
   std::vector<int32_t> ri, ci;
   compact_ids(barcode, nnz, &c->row_ids, &ri);
   compact_ids(gene, nnz, &c->col_ids, &ci);
+  tm.lap("compact ids");
   c->rows = (int64_t)c->row_ids.size();
   c->cols = (int64_t)c->col_ids.size();
-  // counting sort by row
-  std::vector<int64_t> start((size_t)c->rows + 1, 0);
-  for (int64_t i = 0; i < nnz; ++i) ++start[(size_t)ri[(size_t)i] + 1];
-  for (int64_t r = 0; r < c->rows; ++r) start[(size_t)r + 1] += start[(size_t)r];
-  std::vector<int64_t> pos(start.begin(), start.end() - 1);
   struct Ent {
     int32_t col;
     double v;
   };
-  std::vector<Ent> ents((size_t)nnz);
-  for (int64_t i = 0; i < nnz; ++i) {
-    int64_t& p = pos[(size_t)ri[(size_t)i]];
-    ents[(size_t)p++] = Ent{ci[(size_t)i], val[(size_t)i]};
-  }
-  // per-row: sort by column (stable, so duplicates keep file order), average duplicates
-  c->rowptr.assign((size_t)c->rows + 1, 0);
-  c->colidx.reserve((size_t)nnz);
-  c->values64.reserve((size_t)nnz);
-  for (int64_t r = 0; r < c->rows; ++r) {
-    Ent* b = ents.data() + start[(size_t)r];
-    Ent* e = ents.data() + start[(size_t)r + 1];
-    std::stable_sort(b, e, [](const Ent& x, const Ent& y) { return x.col < y.col; });
-    for (Ent* q = b; q < e;) {
-      Ent* g = q;
-      double sum = 0.0;
-      int64_t cnt = 0;
-      while (g < e && g->col == q->col) {
-        sum += g->v;
-        ++cnt;
-        ++g;
-      }
-      c->colidx.push_back(q->col);
-      c->values64.push_back(cnt == 1 ? sum : sum / (double)cnt);
-      q = g;
+  std::vector<int64_t> start((size_t)c->rows + 1, 0);
+  std::unique_ptr<Ent[]> ents_mem(new Ent[(size_t)nnz > 0 ? (size_t)nnz : 1]);  // uninitialised
+  Ent* const ents = ents_mem.get();
+  // 10x files are barcode-major: when the compact row index never decreases the entries are
+  // already grouped by row in file order and only need copying (in parallel); otherwise a
+  // counting sort by row (stable: duplicates keep file order)
+  bool grouped = true;
+  for (int64_t i = 1; i < nnz; ++i)
+    if (ri[(size_t)i] < ri[(size_t)i - 1]) {
+      grouped = false;
+      break;
     }
-    c->rowptr[(size_t)r + 1] = (int64_t)c->colidx.size();
+  for (int64_t i = 0; i < nnz; ++i) ++start[(size_t)ri[(size_t)i] + 1];
+  for (int64_t r = 0; r < c->rows; ++r) start[(size_t)r + 1] += start[(size_t)r];
+  if (grouped) {
+    parallel_ranges(nnz, nnz > (1 << 18) ? worker_threads() : 1, [&](int64_t a, int64_t b, unsigned) {
+      for (int64_t i = a; i < b; ++i) ents[(size_t)i] = Ent{ci[(size_t)i], val[(size_t)i]};
+    });
+  } else {
+    std::vector<int64_t> pos(start.begin(), start.end() - 1);
+    for (int64_t i = 0; i < nnz; ++i) {
+      int64_t& p = pos[(size_t)ri[(size_t)i]];
+      ents[(size_t)p++] = Ent{ci[(size_t)i], val[(size_t)i]};
+    }
   }
-  c->values.resize(c->values64.size());
-  for (size_t i = 0; i < c->values64.size(); ++i) c->values[i] = (float)c->values64[i];
+  tm.lap(grouped ? "group by row (already grouped)" : "counting sort by row");
+  // per-row: sort by column (stable, so duplicates keep file order), average duplicates.
+  // Rows are independent: pass A sorts (skipped when the row is already strictly ascending, the
+  // normal case of a 10x file) and counts the distinct columns, pass B writes the CSR arrays.
+  const unsigned nt = nnz > (1 << 16) ? worker_threads() : 1;
+  c->rowptr.assign((size_t)c->rows + 1, 0);
+  parallel_ranges(c->rows, nt, [&](int64_t r0, int64_t r1, unsigned) {
+    for (int64_t r = r0; r < r1; ++r) {
+      Ent* b = ents + start[(size_t)r];
+      Ent* e = ents + start[(size_t)r + 1];
+      bool ascending = true;
+      for (Ent* q = b + 1; q < e; ++q)
+        if (q->col <= (q - 1)->col) {
+          ascending = false;
+          break;
+        }
+      int64_t distinct = e - b;
+      if (!ascending) {
+        std::stable_sort(b, e, [](const Ent& x, const Ent& y) { return x.col < y.col; });
+        distinct = (e > b) ? 1 : 0;
+        for (Ent* q = b + 1; q < e; ++q) distinct += (q->col != (q - 1)->col);
+      }
+      c->rowptr[(size_t)r + 1] = distinct;
+    }
+  });
+  for (int64_t r = 0; r < c->rows; ++r) c->rowptr[(size_t)r + 1] += c->rowptr[(size_t)r];
+  const size_t out_nnz = (size_t)c->rowptr[(size_t)c->rows];
+  c->colidx.resize(out_nnz);
+  c->values64.resize(out_nnz);
+  c->values.resize(out_nnz);
+  parallel_ranges(c->rows, nt, [&](int64_t r0, int64_t r1, unsigned) {
+    for (int64_t r = r0; r < r1; ++r) {
+      const Ent* e = ents + start[(size_t)r + 1];
+      size_t o = (size_t)c->rowptr[(size_t)r];
+      for (const Ent* q = ents + start[(size_t)r]; q < e;) {
+        const Ent* g = q;
+        double sum = 0.0;
+        int64_t cnt = 0;
+        while (g < e && g->col == q->col) {
+          sum += g->v;
+          ++cnt;
+          ++g;
+        }
+        const double v = cnt == 1 ? sum : sum / (double)cnt;
+        c->colidx[o] = q->col;
+        c->values64[o] = v;
+        c->values[o] = (float)v;
+        ++o;
+        q = g;
+      }
+    }
+  });
+  tm.lap("row sort + dedup (threads)");
   *out = c;
   return 0;
 }
@@ -246,6 +350,7 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
       return -1;
     }
   }
+  StageTimer tm;
   // skip exactly 3 lines (skiprows=3): banner, comment, dims
   const char* p = data;
   const char* end = data + size;
@@ -254,9 +359,7 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
     p = nl ? nl + 1 : end;
   }
   // chunk the body at line boundaries
-  unsigned nt = std::thread::hardware_concurrency();
-  if (nt == 0) nt = 4;
-  if (nt > 32) nt = 32;
+  unsigned nt = worker_threads();
   const size_t body = (size_t)(end - p);
   if (body < (1u << 20)) nt = 1;
   std::vector<const char*> cut(nt + 1);
@@ -268,35 +371,54 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
     const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
     cut[t] = nl ? nl + 1 : end;
   }
-  std::vector<Triplets> parts(nt);
+  // pass 1: an upper bound of every chunk's entry count (newlines + 1) gives each thread its
+  // slice of the triplet arrays; pass 2 parses straight into the slices (no per-thread vectors,
+  // no concatenation)
+  std::vector<int64_t> cap(nt, 0), off(nt + 1, 0), got(nt, 0);
+  {
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < nt; ++t)
+      threads.emplace_back([&, t] { cap[t] = count_newlines(cut[t], cut[t + 1]) + 1; });
+    for (auto& th : threads) th.join();
+  }
+  for (unsigned t = 0; t < nt; ++t) off[t + 1] = off[t] + cap[t];
+  // (uninitialised: every used element is written by the parser)
+  const size_t cap_total = (size_t)off[nt] > 0 ? (size_t)off[nt] : 1;
+  std::unique_ptr<int64_t[]> gene_mem(new int64_t[cap_total]), barcode_mem(new int64_t[cap_total]);
+  std::unique_ptr<double[]> val_mem(new double[cap_total]);
+  int64_t* const gene = gene_mem.get();
+  int64_t* const barcode = barcode_mem.get();
+  double* const val = val_mem.get();
   std::vector<std::string> errs(nt);
-  std::vector<char> oks(nt, 1);
-  std::vector<std::thread> threads;
-  for (unsigned t = 0; t < nt; ++t)
-    threads.emplace_back([&, t] { oks[t] = parse_chunk(cut[t], cut[t + 1], &parts[t], &errs[t]); });
-  for (auto& th : threads) th.join();
+  {
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < nt; ++t)
+      threads.emplace_back([&, t] {
+        got[t] = parse_chunk(cut[t], cut[t + 1], gene + off[t], barcode + off[t],
+                             val + off[t], &errs[t]);
+      });
+    for (auto& th : threads) th.join();
+  }
+  tm.lap("count + parse (threads)");
   if (data) munmap((void*)data, size);
   close(fd);
   for (unsigned t = 0; t < nt; ++t)
-    if (!oks[t]) {
+    if (got[t] < 0) {
       cc::set_error("cc_mtx_load_csr: malformed line in %s: '%s'", path, errs[t].c_str());
       return -1;
     }
-  size_t nnz = 0;
-  for (auto& q : parts) nnz += q.val.size();
-  Triplets all;
-  all.gene.reserve(nnz);
-  all.barcode.reserve(nnz);
-  all.val.reserve(nnz);
-  for (auto& q : parts) {
-    all.gene.insert(all.gene.end(), q.gene.begin(), q.gene.end());
-    all.barcode.insert(all.barcode.end(), q.barcode.begin(), q.barcode.end());
-    all.val.insert(all.val.end(), q.val.begin(), q.val.end());
-    Triplets().gene.swap(q.gene);
-    Triplets().barcode.swap(q.barcode);
-    Triplets().val.swap(q.val);
+  // close the gaps blank lines / the +1 left between the slices (normally a few elements)
+  int64_t nnz = got[0];
+  for (unsigned t = 1; t < nt; ++t) {
+    if (off[t] != nnz && got[t] > 0) {
+      memmove(gene + nnz, gene + off[t], (size_t)got[t] * sizeof(int64_t));
+      memmove(barcode + nnz, barcode + off[t], (size_t)got[t] * sizeof(int64_t));
+      memmove(val + nnz, val + off[t], (size_t)got[t] * sizeof(double));
+    }
+    nnz += got[t];
   }
-  return build_csr(all.gene.data(), all.barcode.data(), all.val.data(), (int64_t)nnz, out);
+  tm.lap("close gaps");
+  return build_csr(gene, barcode, val, nnz, out);
 }
 
 extern "C" void cc_csr_destroy(cc_csr* csr) { delete csr; }
