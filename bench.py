@@ -335,6 +335,33 @@ def run_ours(args):
     ms_resident = max_over_ranks(ev0.elapsed_time(ev1))
     last_losses = [float(v) for v in losses]
 
+    # ---- the same step at the reference's default batch of 128 cells (src/__main__.py:44):
+    # weight / optimiser streaming regime, HBM-bound; device-resident, same engine
+    small = None
+    if (world == 1 and args.small_batch and args.small_batch < B and graphed is not None
+            and not classify):
+        Bs = args.small_batch
+        gs_small = e.capture_step((rowptr, colidx, values), args.genes, Bs, latents="device")
+        idx_small = idx_all[:, :Bs].contiguous()
+        for i in range(3):
+            gs_small.idx.copy_(idx_small[i % n_pre], non_blocking=True)
+            gs_small.replay()
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            gs_small.idx.copy_(idx_small[i % n_pre], non_blocking=True)
+            gs_small.replay()
+        e.join()
+        ev1.record()
+        barrier()
+        ms_small = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        small = {"batch_per_gpu": Bs, "value": Bs * world / (ms_small / 1e3), "unit": "cells/s",
+                 "ms_per_step": ms_small,
+                 "note": "reference default batch; the step streams every weight and optimiser "
+                         "slot once per update (26 B/parameter), so it is HBM-bound: "
+                         f"{1.843e9 * 26 / 1e9:.1f} GB per step at the measured HBM peak = "
+                         f"{1.843e9 * 26 / (peaks()['hbm_gbs'] * 1e9) * 1e3:.1f} ms"}
+
     # ---- end to end through the public API (host sampling, H2D indices+priors, D2H losses)
     for _ in range(min(2, args.warmup)):
         [float(v) for v in net.trainings_step(trainer.sample_cell_data())]
@@ -532,6 +559,7 @@ def run_ours(args):
                         "numpy sampling, pageable->device copy of the batch indices and priors, "
                         "three loss floats read back per step"},
         "e2e_dense_host_batch": dense_e2e,
+        "reference_batch": small,
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "tensor",
@@ -826,6 +854,8 @@ def main():
                          "encode-only pass over --encode-cells cells (configs[4]); loader: "
                          "load_matrix on a synthetic .mtx (host C++ vs the reference's pandas)")
     ap.add_argument("--encode-cells", type=int, default=1_000_000)
+    ap.add_argument("--small-batch", type=int, default=128,
+                    help="also time the step at this (the reference's default) batch; 0: skip")
     ap.add_argument("--dense-e2e-steps", type=int, default=3,
                     help="steps of the dense-host-batch end-to-end variant (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
