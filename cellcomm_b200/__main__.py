@@ -1,110 +1,98 @@
-"""`python3 src` / `python3 -m cellcomm_b200` entry point (reference src/__main__.py:30-99):
-train ContinuousCellBiGan on one of the GSE122930 sources with the print / CSV / MongoDB
-interceptors, or `convert <matrix.mtx> <cells.csv>`.  Same module constants, same log-dir
-rule (`logs/<MM-DD-HHMM>_<RUN_ID>_e<Z>` must not exist), SIGINT exits 0.
+"""Entry point: `python3 src` / `python3 -m cellcomm_b200`.
 
-Extra, optional environment knobs (the reference has none): CELLCOMM_DATA_DIR (where the
-`*_matrix.mtx`, `*_barcodes.tsv`, `*_genes.tsv` live; default `<repo>/data`),
-CELLCOMM_ITERATIONS, CELLCOMM_BATCH_SIZE.
+Behaviour of the reference's src/__main__.py:30-99: with no argument train
+`ContinuousCellBiGan` (Z = 3, batch 128, one iteration) on the second GSE122930 source with
+the stdout / CSV / MongoDB interceptors; `convert <matrix.mtx> <cells.csv>` writes the dense
+cell file `load_cells` reads.  The run's log directory `logs/<MM-DD-HHMM>_<RUN_ID>_e<Z>` must
+not exist yet; Ctrl-C ends the process with exit status 0.
+
+The module-level names other code may import are kept (`SOURCE_IDS`, `SOURCES`, `RUN_ID`,
+`DATA_SOURCES`, `run_training`, `create_interceptors`, `check_log_dir`,
+`store_converted_cell_file`).  Environment knobs the reference does not have:
+CELLCOMM_DATA_DIR (directory of the `<source>_matrix.mtx / _barcodes.tsv / _genes.tsv`
+files, default `<repo>/data`), CELLCOMM_ITERATIONS, CELLCOMM_BATCH_SIZE.
 """
 import os
-import pathlib
 import signal
 import sys
-from datetime import datetime
+import time
 
+from . import intercepts
 from .cell_type_training import CellTraining, load_matrix
-from .intercepts import (DbRecorder, SinkIntercepts, combined_interceptors, offset_iterations,
-                         print_losses, skip_iterations)
 
-DATA_DIR = os.environ.get('CELLCOMM_DATA_DIR',
-                          os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'data'))
+ENCODING_SIZE = 3
+DATA_DIR = os.environ.get('CELLCOMM_DATA_DIR') or os.path.normpath(
+    os.path.join(os.path.dirname(os.path.abspath(__file__)), os.pardir, 'data'))
+SOURCE_FILES = {'matrix': 'mtx', 'barcodes': 'tsv', 'genes': 'tsv'}
 
-
-def data_file(file):
-    return os.path.join(DATA_DIR, file)
-
-
-def log_file(log_file_):
-    return os.path.join('logs', log_file_)
-
-
-def build_source(source_id):
-    return {kind: data_file(f'{source_id}_{kind}.{ext}')
-            for kind, ext in (('matrix', 'mtx'), ('barcodes', 'tsv'), ('genes', 'tsv'))}
-
-
-SOURCE_IDS = [
-    'GSE122930_TAC_1_week_repA+B',
-    'GSE122930_TAC_4_weeks_repA+B',
-    'GSE122930_Sham_1_week',
-    'GSE122930_Sham_4_weeks_repA+B'
-]
-
-SOURCES = [build_source(src) for src in SOURCE_IDS]
-
+SOURCE_IDS = [f'GSE122930_{name}' for name in
+              ('TAC_1_week_repA+B', 'TAC_4_weeks_repA+B', 'Sham_1_week', 'Sham_4_weeks_repA+B')]
+SOURCES = [{kind: os.path.join(DATA_DIR, f'{sid}_{kind}.{ext}') for kind, ext in SOURCE_FILES.items()}
+           for sid in SOURCE_IDS]
 RUN_ID = 'test'
 DATA_SOURCES = SOURCES[1]
-LOG_ID_TEMPLATE = '{}_' + RUN_ID + '_e{}'
 
 
-def run_training(batch_size=128):
-    data_source = load_matrix(DATA_SOURCES['matrix'], verbose=True)
-    encoding_size = 3
-
-    trainer = CellTraining(data_source, batch_size=batch_size, encoding_size=encoding_size)
-    interceptors = create_interceptors(encoding_size, trainer, DATA_SOURCES)
-    trainer.run(int(os.environ.get('CELLCOMM_ITERATIONS', '1')), interceptors)
-
-
-def create_interceptors(encoding_size, trainer, sources):
-    now = datetime.now().strftime('%m-%d-%H%M')
-    full_run_id = LOG_ID_TEMPLATE.format(now, encoding_size)
-    log_dir = log_file(full_run_id)
-    check_log_dir(log_dir)
-
-    sink = SinkIntercepts(log_dir)
-    db_rec = DbRecorder(RUN_ID, sources)
-    db_rec.setup()
-    return combined_interceptors([
-        print_losses(full_run_id),
-        sink.save_losses(),
-        offset_iterations(0, skip_iterations(1, db_rec.create_interceptor(trainer)))
-    ])
+def _env_int(name, default):
+    return int(os.environ.get(name, default))
 
 
 def check_log_dir(log_dir):
-    log_path = pathlib.Path(log_dir)
-    if log_path.exists():
+    """Create the run's log directory; an existing one means the run id was used before."""
+    if os.path.exists(log_dir):
         raise AssertionError(f'duplicate run-id, log-dir: {log_dir}')
-    log_path.mkdir(parents=True)
+    os.makedirs(log_dir)
+
+
+def create_interceptors(encoding_size, trainer, sources):
+    """stdout losses + losses.csv + the MongoDB recorder (every iteration from the first)."""
+    full_run_id = f"{time.strftime('%m-%d-%H%M')}_{RUN_ID}_e{encoding_size}"
+    log_dir = os.path.join('logs', full_run_id)
+    check_log_dir(log_dir)
+    recorder = intercepts.DbRecorder(RUN_ID, sources)
+    recorder.setup()
+    record = intercepts.skip_iterations(1, recorder.create_interceptor(trainer))
+    return intercepts.combined_interceptors((
+        intercepts.print_losses(full_run_id),
+        intercepts.SinkIntercepts(log_dir).save_losses(),
+        intercepts.offset_iterations(0, record),
+    ))
+
+
+def run_training(batch_size=128):
+    cells = load_matrix(DATA_SOURCES['matrix'], verbose=True)
+    trainer = CellTraining(cells, batch_size=batch_size, encoding_size=ENCODING_SIZE)
+    trainer.run(_env_int('CELLCOMM_ITERATIONS', 1),
+                create_interceptors(ENCODING_SIZE, trainer, DATA_SOURCES))
 
 
 def store_converted_cell_file(matrix_file, cell_file):
     print('converting matrix file:')
-    df = load_matrix(matrix_file, verbose=True)
+    cells = load_matrix(matrix_file, verbose=True)
     print('storing cell file:', cell_file, '... ', end='', flush=True)
-    df.to_csv(cell_file)
+    cells.to_csv(cell_file)
     print('done')
 
 
-def signal_handler(_, __):
+def _stop(_signum, _frame):
     print('\tstopped')
     sys.exit(0)
 
 
 def main(argv):
-    signal.signal(signal.SIGINT, signal_handler)
-    if len(argv) > 1:
-        cmd = argv[1]
-        if cmd == 'convert':
-            assert len(argv) == 4, \
-                'required parameters missing: convert <source-matrix-file> <convert-target-file>'
-            store_converted_cell_file(argv[2], argv[3])
-        else:
-            print('unrecognised command:', cmd)
-    else:
-        run_training(int(os.environ.get('CELLCOMM_BATCH_SIZE', '128')))
+    signal.signal(signal.SIGINT, _stop)
+    commands = {'convert': (2, store_converted_cell_file,
+                            'convert <source-matrix-file> <convert-target-file>')}
+    if len(argv) < 2:
+        run_training(_env_int('CELLCOMM_BATCH_SIZE', 128))
+        return
+    name, params = argv[1], argv[2:]
+    if name not in commands:
+        print('unrecognised command:', name)
+        return
+    n_params, handler, usage = commands[name]
+    assert len(params) == n_params, f'required parameters missing: {usage}'
+    handler(*params)
 
 
 if __name__ == '__main__':

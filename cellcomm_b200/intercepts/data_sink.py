@@ -1,6 +1,10 @@
-"""CSV sink with batched appends (reference src/intercepts/data_sink.py:15-60): one
-`<log_dir>/<graph>.csv` per graph id, a header line on registration, the same three
-AssertionError messages."""
+"""CSV sink behind `SinkIntercepts` (API of the reference's src/intercepts/data_sink.py:15-60).
+
+Every graph id owns one file `<log_dir>/<graph id>.csv`: registering the graph writes the
+header row, `add_data` buffers a row and flushes once `batch_size` rows are waiting,
+`drain_data` flushes everything (the owner hooks it to `atexit`).  The three AssertionError
+texts callers can see are the reference's.
+"""
 from typing import Any, Iterable
 
 DEFAULT_LOG_DIR = 'logs'
@@ -8,43 +12,49 @@ DEFAULT_BATCH_SIZE = 1
 
 
 def csv_line(values):
-    return ','.join(str(s) for s in values) + '\n'
+    """One CSV row: `str()` of every value, comma separated, newline terminated."""
+    return ','.join(map(str, values)) + '\n'
+
+
+class _Series:
+    """One CSV file: fixed column count, rows buffered until flushed."""
+
+    def __init__(self, path, columns):
+        self.path, self.columns, self.pending = path, columns, []
+
+    def write(self, text):
+        with open(self.path, 'a+') as out:
+            out.write(text)
+
+    def flush(self):
+        if self.pending:
+            self.write(''.join(self.pending))
+            self.pending = []
 
 
 class DataSink:
     def __init__(self, log_dir=DEFAULT_LOG_DIR, batch_size=DEFAULT_BATCH_SIZE):
-        self._log_dir = log_dir
-        self._batch_size = batch_size
-        self._graphs = {}      # graph id -> {'file', 'lines', 'size'}
+        self._log_dir, self._batch_size = log_dir, batch_size
+        self._series = {}
 
     def add_graph_header(self, graph_id, fields: Iterable[Any]):
-        if graph_id in self._graphs:
+        if graph_id in self._series:
             raise AssertionError(f'duplicate graph name: {graph_id}')
-        fields = list(fields)
-        self._graphs[graph_id] = {'file': f'{self._log_dir}/{graph_id}.csv', 'lines': [],
-                                  'size': len(fields)}
-        self._append(graph_id, csv_line(fields))
+        names = list(fields)
+        series = _Series(f'{self._log_dir}/{graph_id}.csv', len(names))
+        self._series[graph_id] = series
+        series.write(csv_line(names))
 
     def add_data(self, graph_id, values: Iterable[Any]):
-        if graph_id not in self._graphs:
+        series = self._series.get(graph_id)
+        if series is None:
             raise AssertionError(f'unknown graph: {graph_id}')
-        graph = self._graphs[graph_id]
-        if not len(values) == graph['size']:
-            raise AssertionError(f'expected {graph["size"]} values, received: {values}')
-        graph['lines'].append(csv_line(values))
-        if len(graph['lines']) >= self._batch_size:
-            self._drain(graph_id)
+        if len(values) != series.columns:
+            raise AssertionError(f'expected {series.columns} values, received: {values}')
+        series.pending.append(csv_line(values))
+        if len(series.pending) >= self._batch_size:
+            series.flush()
 
     def drain_data(self):
-        for graph_id in self._graphs:
-            self._drain(graph_id)
-
-    def _drain(self, graph_id):
-        lines = self._graphs[graph_id]['lines']
-        if lines:
-            self._append(graph_id, ''.join(lines))
-            lines.clear()
-
-    def _append(self, graph_id, text):
-        with open(self._graphs[graph_id]['file'], 'a+') as f:
-            f.write(text)
+        for series in self._series.values():
+            series.flush()
