@@ -157,3 +157,59 @@ def test_gradient_buckets_tile_the_kernel_region(monkeypatch, bucket_elems):
             assert (bk["end"] - bk["start"]) % 64 == 0 and bk["pieces"] >= 1
         if bucket_elems == 1 << 11:
             assert max(len(p) for p in net.pieces.values()) >= 2     # big kernels were cut
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_routed_gradient_addresses_meet_the_optimiser_shards(monkeypatch, world):
+    """Host-side addressing of the peer-memory data-parallel path, without a GPU: replay what
+    the routed wgrad epilogue does with the (world, shard, off0, bases) tuples `Net._route`
+    hands to cc_gemm (element rel = off0 + row*ld + col goes to bases[rel // shard] + 4*rel)
+    on fake per-rank staging arrays, then check that the ranges `_launch_bucket` gives to
+    cc_peer_rmsprop (this rank's 1/world slice of every bucket, read from staging slot q for
+    every source rank q) hold exactly rank q's values for every kernel element."""
+    monkeypatch.setattr(eng, "_BUCKET_ELEMS", 1 << 12)
+    e = eng.BiGanEngine("cont", 3, 300, max_batch=4, device="cpu", seed=0)
+    net = e.D
+    n_flat = net.n_flat
+    BASE = 1 << 44                                  # fake device address of rank r's staging
+    stage = [np.full(world * n_flat, -1.0) for _ in range(world)]
+
+    class FakeDist:
+        world_size = world
+        rank = 0
+
+    kernel_elems = np.zeros(n_flat, dtype=bool)
+    for me in range(world):
+        FakeDist.rank = me
+        net.dist = FakeDist
+        net.peer = {"stage": [r * BASE for r in range(world)]}
+        for pieces in net.pieces.values():
+            for pc in pieces:
+                W, shard, off0, bases = net._route(pc)
+                L = net.layers[pc["layer"]]
+                rows, ld, N = pc["hi"] - pc["lo"], L["ld"], L["N"]
+                r_idx, c_idx = np.meshgrid(np.arange(rows), np.arange(N), indexing="ij")
+                rel = off0 + r_idx * ld + c_idx
+                owner = np.minimum(rel // shard, W - 1)
+                for r in range(world):
+                    sel = owner == r
+                    addr = bases[r] + 4 * rel[sel]               # byte address on rank r
+                    slot_elem = (addr - r * BASE) // 4            # element of rank r's staging
+                    flat = pc["bucket"]["start"] + rel[sel]
+                    assert np.all(slot_elem == me * n_flat + flat)
+                    stage[r][slot_elem] = me * 1e9 + flat         # "rank me's gradient value"
+                    kernel_elems[flat] = True
+    # optimiser side: rank r updates [start + r*n, start + (r+1)*n) of every bucket
+    covered = np.zeros(n_flat, dtype=bool)
+    for bk in net.buckets:
+        n = (bk["end"] - bk["start"]) // world
+        assert n * world == bk["end"] - bk["start"] and n % 8 == 0
+        for r in range(world):
+            lo = bk["start"] + r * n
+            offs = np.arange(lo, lo + n)
+            live = kernel_elems[offs]                              # (padding is never written)
+            for q in range(world):
+                got = stage[r][q * n_flat + offs]
+                assert np.all(got[live] == q * 1e9 + offs[live])
+            covered[offs] = True
+    assert np.all(covered[kernel_elems])
