@@ -13,10 +13,10 @@ import time
 from .plot_intercepts import PlotIntercepts
 from .sink_intercepts import SinkIntercepts
 from .db_recorder import DbRecorder
-from .encoding_files import EncodingFiles
+from .encoding_files import Checkpoints, EncodingFiles
 
 __all__ = ["combined_interceptors", "skip_iterations", "offset_iterations", "print_losses",
-           "PlotIntercepts", "SinkIntercepts", "DbRecorder", "EncodingFiles"]
+           "PlotIntercepts", "SinkIntercepts", "DbRecorder", "EncodingFiles", "Checkpoints"]
 
 LOSS_LINE = ("[{stamp}] {run} it: {it:6}  TOT: {total:6.3f}  G-L: {g:6.3f}  E-L: {e:6.3f}  "
              "D-L: {d:6.3f}")

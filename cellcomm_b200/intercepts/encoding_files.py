@@ -42,3 +42,30 @@ def load_encodings(log_dir, iteration):
     their x255)."""
     with open(EncodingFiles(log_dir).path(iteration), 'rb') as f:
         return pickle.load(f)
+
+
+class Checkpoints:
+    """Interceptor that saves `network.save_checkpoint()` every `every` iterations to
+    `<log_dir>/checkpoint.npz` (atomic replace), and `resume(trainer)` that restores the newest
+    one before a run.  The reference persists nothing but encodings and loss CSVs (SURVEY.md 5);
+    this is row f4 of its "next" list wired into the interceptor mechanism."""
+
+    def __init__(self, log_dir, every=1):
+        self.path = os.path.join(log_dir, 'checkpoint.npz')
+        self.every = max(1, int(every))
+
+    def resume(self, trainer):
+        """-> True when a checkpoint was found and loaded."""
+        if not os.path.exists(self.path):
+            return False
+        trainer.network.load_checkpoint(self.path)
+        return True
+
+    def create_interceptor(self, trainer):
+        os.makedirs(os.path.dirname(self.path) or '.', exist_ok=True)
+
+        def intercept(it, _):
+            if (it + 1) % self.every == 0:
+                trainer.network.save_checkpoint(self.path)
+
+        return intercept

@@ -123,3 +123,30 @@ def test_enc_files_length_assertion(tmp_path):
     intercept = EncodingFiles(str(tmp_path)).create_interceptor(trainer)
     with pytest.raises(AssertionError, match="different length: 4 != 5"):
         intercept(0, None)
+
+
+class _CkptNet:
+    def __init__(self):
+        self.saved, self.loaded = [], []
+
+    def save_checkpoint(self, path):
+        self.saved.append(path)
+        open(path, "wb").write(b"x")
+
+    def load_checkpoint(self, path):
+        self.loaded.append(path)
+
+
+def test_checkpoint_interceptor_saves_every_n_and_resumes(tmp_path):
+    from cellcomm_b200.intercepts import Checkpoints
+
+    class T:
+        network = _CkptNet()
+
+    ck = Checkpoints(str(tmp_path / "logs" / "r"), every=2)
+    assert ck.resume(T) is False and T.network.loaded == []
+    intercept = ck.create_interceptor(T)
+    for it in range(5):
+        intercept(it, (0.0, 0.0, 0.0))
+    assert len(T.network.saved) == 2 and T.network.saved[0].endswith("checkpoint.npz")   # it 1, 3
+    assert ck.resume(T) is True and T.network.loaded == [ck.path]
