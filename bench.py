@@ -27,9 +27,40 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's debug stream (the version banner it prints at
-# NCCL_DEBUG=VERSION / WARN included) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
+class stdout_to_stderr:
+    """stdout carries exactly one JSON line: while the process group / NCCL communicators come
+    up, file descriptor 1 points at stderr, so the "NCCL version ..." banner that the library
+    writes straight to stdout ends up there (measured: NCCL_DEBUG_FILE does not catch it)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        try:                                     # C stdio buffers of the libraries as well
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def init_distributed(dev):
+    """NCCL process group + first collective (creates the communicator) with stdout parked."""
+    import torch
+    import torch.distributed as dist
+    with stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+
 
 GENES, CELLS, Z = 33694, 30000, 3
 FLOP_PER_CELL_TRAIN = 13.237e9      # SURVEY.md App. B (dense-equivalent 2*M*N*K, Continuous)
@@ -240,7 +271,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_distributed(dev)
     B = args.batch
 
     def barrier():
@@ -636,7 +667,7 @@ def run_encode(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_distributed(dev)
 
     def barrier():
         if world > 1:
