@@ -41,3 +41,18 @@ def test_loader_workload_matches_the_reference_body():
     d = _run("--workload", "loader", "--loader-cells", "40", "--genes", "600", "--steps", "1")
     assert d["metric"] == "load_matrix nnz/sec" and d["matches_reference_pandas_body"] is True
     assert d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
+
+
+def test_stdout_is_parked_on_stderr_while_libraries_initialise():
+    """bench.stdout_to_stderr: C-level (buffered printf) and Python-level writes made inside the
+    block land on stderr; stdout keeps only what is printed afterwards."""
+    code = (
+        "import sys, ctypes; sys.path.insert(0, %r); import bench\n"
+        "libc = ctypes.CDLL(None)\n"
+        "with bench.stdout_to_stderr():\n"
+        "    libc.printf(b'NCCL version x.y\\n'); print('python banner')\n"
+        "print('{\"ok\": 1}', flush=True)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"ok": 1}\n'
+    assert "NCCL version x.y" in r.stderr and "python banner" in r.stderr
