@@ -69,6 +69,13 @@ SIGNATURES = {
     "cc_csr_values64": (vp, [vp]),
     "cc_csr_row_ids": (vp, [vp]),
     "cc_csr_col_ids": (vp, [vp]),
+    "cc_mtx_load_coo": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "cc_coo_destroy": (None, [vp]),
+    "cc_coo_nnz": (c_i64, [vp]),
+    "cc_coo_gene": (vp, [vp]),
+    "cc_coo_barcode": (vp, [vp]),
+    "cc_coo_value": (vp, [vp]),
+    "cc_coo_build_csr": (C.c_int, [vp, C.POINTER(vp)]),
     "cc_gather_rows": (C.c_int, [vp, vp, vp, vp, c_i64, c_i64, c_i64, vp, c_i64, vp, c_i64, vp]),
     "cc_gemm": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "cc_gemm_workspace_elems": (c_i64, [c_i32, c_i32]),

@@ -30,19 +30,21 @@ gather_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__
     if (out16 != nullptr) {
       bf16* orow = out16 + i * ld16;
       if (use_smem) {
-        // ld16 % 8 == 0 is guaranteed by the host wrapper on this path
-        const long long nvec = ld16 / 8;
+        // rows are 16-byte aligned on this path (host wrapper).  Only columns [0, n_cols) are
+        // written, so `out16` may be a column slice of a wider buffer.
+        const long long nvec = n_cols / 8, nz = (n_cols + 7) / 8;
         uint4* s4 = reinterpret_cast<uint4*>(srow);
-        for (long long v = tid; v < nvec; v += GATHER_THREADS) s4[v] = make_uint4(0, 0, 0, 0);
+        for (long long v = tid; v < nz; v += GATHER_THREADS) s4[v] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         for (long long e = beg + tid; e < end; e += GATHER_THREADS)
           srow[colidx[e]] = f2bf(values[e]);
         __syncthreads();
         uint4* o4 = reinterpret_cast<uint4*>(orow);
         for (long long v = tid; v < nvec; v += GATHER_THREADS) o4[v] = s4[v];
+        for (long long c = nvec * 8 + tid; c < n_cols; c += GATHER_THREADS) orow[c] = srow[c];
         __syncthreads();
       } else {
-        for (long long c = tid; c < ld16; c += GATHER_THREADS) orow[c] = f2bf(0.f);
+        for (long long c = tid; c < n_cols; c += GATHER_THREADS) orow[c] = f2bf(0.f);
         __syncthreads();
         for (long long e = beg + tid; e < end; e += GATHER_THREADS)
           orow[colidx[e]] = f2bf(values[e]);
@@ -51,7 +53,7 @@ gather_rows_kernel(const long long* __restrict__ rowptr, const int* __restrict__
     }
     if (out32 != nullptr) {
       float* orow = out32 + i * ld32;
-      for (long long c = tid; c < ld32; c += GATHER_THREADS) orow[c] = 0.f;
+      for (long long c = tid; c < n_cols; c += GATHER_THREADS) orow[c] = 0.f;
       __syncthreads();
       for (long long e = beg + tid; e < end; e += GATHER_THREADS) orow[colidx[e]] = values[e];
       __syncthreads();
@@ -83,9 +85,9 @@ extern "C" int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_d
   size_t smem = 0;
   int use_smem = 0;
   if (out16 != nullptr && ld16 % 8 == 0 && (((uintptr_t)out16) & 15) == 0 &&
-      (size_t)ld16 * 2 <= (size_t)max_smem) {
+      (size_t)(n_cols + 7) / 8 * 16 <= (size_t)max_smem) {
     use_smem = 1;
-    smem = (size_t)ld16 * 2;
+    smem = (size_t)(n_cols + 7) / 8 * 16;
   }
   // rows per CTA: grid-stride; cap the grid at a few waves so tiny rows do not over-launch
   long long grid = n_rows;

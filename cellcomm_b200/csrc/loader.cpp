@@ -324,20 +324,23 @@ extern "C" int cc_coo_to_csr(const int64_t* gene, const int64_t* barcode, const 
   return build_csr(gene, barcode, val, nnz, out);
 }
 
-extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
-  if (path == nullptr || out == nullptr) {
-    cc::set_error("cc_mtx_load_csr: bad arguments");
-    return -1;
-  }
+// The file's triplets in FILE ORDER (1-based ids as written), parsed by all host threads.
+struct Triplets {
+  std::unique_ptr<int64_t[]> gene, barcode;
+  std::unique_ptr<double[]> val;
+  int64_t nnz = 0;
+};
+
+static int parse_mtx_file(const char* path, Triplets* t_out, StageTimer& tm) {
   int fd = open(path, O_RDONLY);
   if (fd < 0) {
-    cc::set_error("cc_mtx_load_csr: cannot open %s: %s", path, strerror(errno));
+    cc::set_error("cc_mtx_load: cannot open %s: %s", path, strerror(errno));
     return -1;
   }
   struct stat sb;
   if (fstat(fd, &sb) != 0) {
     close(fd);
-    cc::set_error("cc_mtx_load_csr: fstat failed on %s", path);
+    cc::set_error("cc_mtx_load: fstat failed on %s", path);
     return -1;
   }
   const size_t size = (size_t)sb.st_size;
@@ -346,11 +349,10 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
     data = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
     if (data == MAP_FAILED) {
       close(fd);
-      cc::set_error("cc_mtx_load_csr: mmap failed on %s", path);
+      cc::set_error("cc_mtx_load: mmap failed on %s", path);
       return -1;
     }
   }
-  StageTimer tm;
   // skip exactly 3 lines (skiprows=3): banner, comment, dims
   const char* p = data;
   const char* end = data + size;
@@ -404,7 +406,7 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
   close(fd);
   for (unsigned t = 0; t < nt; ++t)
     if (got[t] < 0) {
-      cc::set_error("cc_mtx_load_csr: malformed line in %s: '%s'", path, errs[t].c_str());
+      cc::set_error("cc_mtx_load: malformed line in %s: '%s'", path, errs[t].c_str());
       return -1;
     }
   // close the gaps blank lines / the +1 left between the slices (normally a few elements)
@@ -418,7 +420,51 @@ extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
     nnz += got[t];
   }
   tm.lap("close gaps");
-  return build_csr(gene, barcode, val, nnz, out);
+  t_out->gene = std::move(gene_mem);
+  t_out->barcode = std::move(barcode_mem);
+  t_out->val = std::move(val_mem);
+  t_out->nnz = nnz;
+  return 0;
+}
+
+extern "C" int cc_mtx_load_csr(const char* path, cc_csr** out) {
+  if (path == nullptr || out == nullptr) {
+    cc::set_error("cc_mtx_load_csr: bad arguments");
+    return -1;
+  }
+  StageTimer tm;
+  Triplets t;
+  if (int rc = parse_mtx_file(path, &t, tm)) return rc;
+  return build_csr(t.gene.get(), t.barcode.get(), t.val.get(), t.nnz, out);
+}
+
+// ---- triplets in file order (the cells / genes importer groups on first appearance) ----
+struct cc_coo {
+  Triplets t;
+};
+
+extern "C" int cc_mtx_load_coo(const char* path, cc_coo** out) {
+  if (path == nullptr || out == nullptr) {
+    cc::set_error("cc_mtx_load_coo: bad arguments");
+    return -1;
+  }
+  StageTimer tm;
+  std::unique_ptr<cc_coo> c(new cc_coo);
+  if (int rc = parse_mtx_file(path, &c->t, tm)) return rc;
+  *out = c.release();
+  return 0;
+}
+extern "C" void cc_coo_destroy(cc_coo* coo) { delete coo; }
+extern "C" int64_t cc_coo_nnz(const cc_coo* c) { return c->t.nnz; }
+extern "C" const int64_t* cc_coo_gene(const cc_coo* c) { return c->t.gene.get(); }
+extern "C" const int64_t* cc_coo_barcode(const cc_coo* c) { return c->t.barcode.get(); }
+extern "C" const double* cc_coo_value(const cc_coo* c) { return c->t.val.get(); }
+extern "C" int cc_coo_build_csr(const cc_coo* c, cc_csr** out) {
+  if (c == nullptr || out == nullptr) {
+    cc::set_error("cc_coo_build_csr: bad arguments");
+    return -1;
+  }
+  return build_csr(c->t.gene.get(), c->t.barcode.get(), c->t.val.get(), c->t.nnz, out);
 }
 
 extern "C" void cc_csr_destroy(cc_csr* csr) { delete csr; }

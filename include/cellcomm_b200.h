@@ -67,6 +67,22 @@ const double* cc_csr_values64(const cc_csr* csr);  /* nnz, the float64 means (Da
 const int64_t* cc_csr_row_ids(const cc_csr* csr);  /* rows, original barcode ids */
 const int64_t* cc_csr_col_ids(const cc_csr* csr);  /* cols, original gene ids */
 
+/* The file's triplets in FILE ORDER (one threaded parse shared with cc_mtx_load_csr).
+ * replaces: load_file(matrix_file, ..., skip=3) + the per-line walk of convert_matrix()
+ *   src/intercepts/import_barcodes.py:4-11,14-45,76 -- cells are runs of equal barcode ids in
+ *   file order, genes are listed in first-seen order, so the importer needs the file order
+ *   that the CSR no longer has. */
+typedef struct cc_coo cc_coo; /* opaque host triplets */
+int cc_mtx_load_coo(const char* path, cc_coo** out);
+void cc_coo_destroy(cc_coo* coo);
+int64_t cc_coo_nnz(const cc_coo* coo);
+/* host views, valid until cc_coo_destroy */
+const int64_t* cc_coo_gene(const cc_coo* coo);    /* nnz, 1-based gene line numbers */
+const int64_t* cc_coo_barcode(const cc_coo* coo); /* nnz, 1-based barcode line numbers */
+const double* cc_coo_value(const cc_coo* coo);    /* nnz */
+/* the CSR of load_matrix() from already parsed triplets (no second read of the file) */
+int cc_coo_build_csr(const cc_coo* coo, cc_csr** out);
+
 /* --------------------------------------------------- batch gather (device)
  * replaces: DataFrame.sample(B) dense row gather, src/cell_type_training.py:37-38,
  * and the DataFrame -> float32 tensor feed of train_on_batch/predict.

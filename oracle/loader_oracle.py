@@ -60,3 +60,26 @@ def find_duplicate_ids(np_coords):
     unique_coords = set(coords)
     all_indices = [[i + 1 for i, x in enumerate(coords) if x == uc] for uc in unique_coords]
     return [ixs for ixs in all_indices if len(ixs) > 1]
+
+
+def convert_matrix_walk(source_id, barcodes, genes_src, matrix):
+    """src/intercepts/import_barcodes.py:14-50 restated: one pass over the `(gene line, barcode
+    line, value)` string triples in file order.  A new cell record starts whenever the barcode
+    column differs from the previous line's (:22-31); every entry appends `{e, m, v=int(p)}` to
+    the current cell (:33-39) and the cell id to the gene record keyed by ensembl id, created
+    on first sight (:40-41); finally each cell's gene list is sorted by value, descending,
+    with Python's stable sort (:43, :48-50).  Gene records come out in first-seen order (:44)."""
+    cells, gene_records, previous = [], {}, None
+    for gene_line, barcode_line, p_val in matrix:
+        if barcode_line != previous:
+            previous = barcode_line
+            cells.append({"sid": source_id, "cid": int(barcode_line),
+                          "n": barcodes[int(barcode_line) - 1], "g": []})
+        ensembl, mgi = genes_src[int(gene_line) - 1][0], genes_src[int(gene_line) - 1][1]
+        cells[-1]["g"].append({"e": ensembl, "m": mgi, "v": int(p_val)})
+        if ensembl not in gene_records:
+            gene_records[ensembl] = {"sid": source_id, "e": ensembl, "m": mgi, "cids": []}
+        gene_records[ensembl]["cids"].append(int(barcode_line))
+    for cell in cells:
+        cell["g"] = sorted(cell["g"], key=lambda g: -g["v"])
+    return cells, list(gene_records.values())
