@@ -11,6 +11,12 @@ The module-level names other code may import are kept (`SOURCE_IDS`, `SOURCES`, 
 `store_converted_cell_file`).  Environment knobs the reference does not have:
 CELLCOMM_DATA_DIR (directory of the `<source>_matrix.mtx / _barcodes.tsv / _genes.tsv`
 files, default `<repo>/data`), CELLCOMM_ITERATIONS, CELLCOMM_BATCH_SIZE.
+
+Data parallel: `torchrun --nproc-per-node N -m cellcomm_b200` (or `... src`) runs one process
+per GPU.  Every rank loads the matrix and trains on its contiguous share of each global
+batch of `batch_size` cells; rank 0 alone creates the log directory and the interceptors
+(stdout, CSV, MongoDB) and the encode-all-cells pass they trigger is sharded by rows over
+all ranks (`CellTraining.run`).
 """
 import os
 import signal
@@ -59,11 +65,35 @@ def create_interceptors(encoding_size, trainer, sources):
     ))
 
 
+def init_data_parallel():
+    """Under torchrun (WORLD_SIZE > 1): bind this process to its GPU and join the NCCL group.
+    -> (rank, world_size)."""
+    world = _env_int('WORLD_SIZE', 1)
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if torch.cuda.is_available() and os.environ.get('CELLCOMM_B200_DEVICE', 'cuda') != 'cpu':
+            local = _env_int('LOCAL_RANK', 0)
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group('gloo')
+    return dist.get_rank(), dist.get_world_size()
+
+
 def run_training(batch_size=128):
-    cells = load_matrix(DATA_SOURCES['matrix'], verbose=True)
+    rank, world = init_data_parallel()
+    cells = load_matrix(DATA_SOURCES['matrix'], verbose=rank == 0)
     trainer = CellTraining(cells, batch_size=batch_size, encoding_size=ENCODING_SIZE)
-    trainer.run(_env_int('CELLCOMM_ITERATIONS', 1),
-                create_interceptors(ENCODING_SIZE, trainer, DATA_SOURCES))
+    # side effects (log directory, Mongo documents, stdout) belong to rank 0 alone
+    interceptors = create_interceptors(ENCODING_SIZE, trainer, DATA_SOURCES) if rank == 0 else None
+    trainer.run(_env_int('CELLCOMM_ITERATIONS', 1), interceptors)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def store_converted_cell_file(matrix_file, cell_file):

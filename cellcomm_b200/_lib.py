@@ -51,6 +51,37 @@ class PeerRmspropDesc(C.Structure):
     ]
 
 
+ENC_MAX_OPS = ENC_MAX_SLOTS = 32
+ENC_DENSE, ENC_SPLIT, ENC_COPY, ENC_BN_INFER, ENC_SOFTMAX = range(5)
+
+
+class EncOp(C.Structure):
+    """cc_enc_op"""
+    _fields_ = [
+        ("kind", c_i32), ("n_in", c_i32),
+        ("in_", c_i32 * 4), ("w_row", c_i32 * 4),
+        ("out", c_i32), ("out2", c_i32),
+        ("width", c_i32), ("act", c_i32),
+        ("w16", vp), ("ldw", c_i64),
+        ("bias", vp),
+        ("gamma", vp), ("beta", vp), ("mean", vp), ("var", vp),
+        ("eps", c_f32),
+    ]
+
+
+class EncodePlan(C.Structure):
+    """cc_encode_plan"""
+    _fields_ = [
+        ("n_cols", c_i32), ("tile_rows", c_i32),
+        ("n_slots", c_i32), ("n_ops", c_i32),
+        ("slot_width", c_i32 * ENC_MAX_SLOTS),
+        ("slot_fp32", c_i32 * ENC_MAX_SLOTS),
+        ("ops", EncOp * ENC_MAX_OPS),
+        ("scratch", vp), ("scratch_bytes", c_i64),
+        ("workspace", vp), ("workspace_elems", c_i64),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/cellcomm_b200.h declares
 SIGNATURES = {
     "cc_last_error": (C.c_char_p, []),
@@ -76,6 +107,8 @@ SIGNATURES = {
     "cc_coo_barcode": (vp, [vp]),
     "cc_coo_value": (vp, [vp]),
     "cc_coo_build_csr": (C.c_int, [vp, C.POINTER(vp)]),
+    "cc_encode_scratch_bytes": (c_i64, [C.POINTER(EncodePlan)]),
+    "cc_encode_stream": (C.c_int, [vp, vp, vp, c_i64, c_i64, C.POINTER(EncodePlan), vp, c_i64, vp]),
     "cc_gather_rows": (C.c_int, [vp, vp, vp, vp, c_i64, c_i64, c_i64, vp, c_i64, vp, c_i64, vp]),
     "cc_gemm": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "cc_gemm_workspace_elems": (c_i64, [c_i32, c_i32]),

@@ -26,7 +26,13 @@ class BasicBiGan:
         self._encoder = encoder_factory(encoding_size, gene_size)
         self._discriminator = discriminator_factory(encoding_size, gene_size)
         self.all_components = self._generator, self._encoder, self._discriminator
+        # the reference snapshots the weights here (src/bigan_basic.py:21-22); engine-backed
+        # components have no weights until the subclass binds them, which then calls
+        # _snapshot_params() itself
         self.__prev_params = None
+        if not any(callable(getattr(c, 'weight_fingerprint', None)) and not _is_mock(c)
+                   for c in self.all_components):
+            self._snapshot_params()
         # private host RNG for the uniform priors: tf.random.uniform in the reference draws
         # from TensorFlow's generator, never from numpy's global state (which the batch sampler
         # and the classify prior use), so the numpy stream stays reference-identical.
@@ -75,6 +81,9 @@ class BasicBiGan:
         true_positives = np.count_nonzero(np.round(result))
 
         return true_positives, batch_size - false_negatives
+
+    def _snapshot_params(self):
+        self.__prev_params = self.__last_layer_params()
 
     def print_params_changes(self, msg):
         curr_params = self.__last_layer_params()

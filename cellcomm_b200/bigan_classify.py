@@ -8,6 +8,7 @@ arithmetic of `train_on_batch` / `predict` runs in libcellcomm_b200.so through
 `BiGanEngine` (tcgen05 GEMMs + tail kernels).  If a factory returns something else (the
 reference's tests inject mocks), no engine is built and only the wiring is available.
 """
+import json
 import os
 from typing import Callable
 
@@ -96,6 +97,8 @@ class ClassifyCellBiGan(BasicBiGan):
                                                [G, E], [z, z], mse, discr_optimizer)
             D.compile(optimizer=discr_optimizer, loss=bce)
             G.trainable, E.trainable, D.trainable = False, False, True
+            self._snapshot_params()             # reference src/bigan_basic.py:21-22
+        self._workers_serving = False
 
     # ------------------------------------------------------------------ priors
     def random_encoding_vector(self, batch_size):
@@ -116,32 +119,158 @@ class ClassifyCellBiGan(BasicBiGan):
     # ------------------------------------------------------------------ the step
     def trainings_step(self, batch):
         """Six updates + two predicts, reference :126-142, as one pass of BiGanEngine.train_step
-        (the sub-step order, freeze pattern and loss bookkeeping live in engine.py)."""
+        (the sub-step order, freeze pattern and loss bookkeeping live in engine.py).
+
+        Data parallel (one process per GPU): every rank calls this with the SAME global batch
+        (`CellTraining.sample_cell_data` draws one `permutation(N)[:B]` on every rank) and
+        draws the same global priors; rank r then works on the contiguous rows
+        [r*B/W, (r+1)*B/W).  BN statistics, gradients and losses are summed over ranks inside
+        the engine, so the step is the reference's step on the global batch."""
         eng = self._require_engine()
         batch_size = len(batch)
         encodings = self.random_encoding_vector(batch_size)
         noise = self.random_uniform_vector(batch_size)
+        lo, hi = self._local_rows(batch_size)
+        if hi - lo != batch_size:
+            encodings, noise = encodings[lo:hi], noise[lo:hi]
+            batch = _rows(batch, lo, hi)
+        n = hi - lo
         if (isinstance(batch, CellBatch) and eng.device.type == "cuda" and
                 eng.peer_graphable() and os.environ.get("CELLCOMM_B200_GRAPH", "1") != "0"):
-            # single GPU: the whole step (gather + ~850 kernels) is one CUDA-graph launch
+            # the whole step (gather + every kernel, in data-parallel runs also the gradient
+            # exchange over peer memory) is one CUDA-graph launch
             gs = eng.capture_step(batch.matrix.device_csr(eng.device), batch.matrix.shape[1],
-                                  batch_size, latents="host")
-            eng.z32[:batch_size].copy_(_as_f32(encodings), non_blocking=True)
-            eng.r32[:batch_size].copy_(_as_f32(noise), non_blocking=True)
+                                  n, latents="host")
+            eng.z32[:n].copy_(_as_f32(encodings), non_blocking=True)
+            eng.r32[:n].copy_(_as_f32(noise), non_blocking=True)
             return gs.replay(batch.positions)
         x16 = self._stage_cells(batch)
-        eng.set_latents(encodings, noise, batch_size)
+        eng.set_latents(encodings, noise, n)
         g_loss, e_loss, d_loss = eng.train_step(x16)
         return g_loss, e_loss, d_loss
 
+    # ------------------------------------------------------------------ data parallel
+    def _world(self):
+        return self._engine.dist.world_size if self._engine is not None else 1
+
+    def _rank(self):
+        return self._engine.dist.rank if self._engine is not None else 0
+
+    def _local_rows(self, n):
+        """This rank's contiguous share [lo, hi) of n global rows."""
+        W = self._world()
+        if W == 1:
+            return 0, n
+        if n % W:
+            raise ValueError(f"data parallel over {W} GPUs needs a batch divisible by {W}, got {n}")
+        r = self._rank()
+        return r * (n // W), (r + 1) * (n // W)
+
+    def is_coordinator(self):
+        """True on the process that runs the interceptors (rank 0; always when single-process)."""
+        return self._rank() == 0
+
+    def sync_host_rng(self):
+        """Give every rank rank 0's host RNG states (numpy's global state, which the batch
+        sampler and the classify prior draw from, and the private prior generator), so all
+        ranks draw the same global batch and priors.  Collective; `CellTraining.run` calls it."""
+        if self._world() == 1:
+            return
+        state = self._engine.dist.broadcast_object(
+            (np.random.get_state(), self._prior_rng.bit_generator.state)
+            if self.is_coordinator() else None)
+        np.random.set_state(state[0])
+        self._prior_rng.bit_generator.state = state[1]
+
+    def broadcast_from_coordinator(self, obj):
+        """rank 0's (picklable) value on every rank.  Collective."""
+        return self._engine.dist.broadcast_object(obj if self.is_coordinator() else None)
+
+    def begin_interceptors(self):
+        """Rank 0, before it runs the interceptors of an iteration: from now on the other ranks
+        sit in `serve()` and execute the collective parts of whatever rank 0 calls."""
+        self._workers_serving = self._world() > 1
+
+    def release_workers(self, failed=False):
+        if getattr(self, "_workers_serving", False):
+            self._workers_serving = False
+            self._engine.dist.broadcast_object(("abort",) if failed else ("release",))
+
+    def serve(self, data):
+        """Ranks != 0 during the interceptors: run this rank's share of every collective
+        operation rank 0 announces -- the row-sharded encode-all-cells pass over `data`
+        (encode: no communication but the final gather of the (N_i, Z) pieces), and the
+        gathers a checkpoint needs -- until rank 0 releases the workers."""
+        dist = self._engine.dist
+        while True:
+            cmd = dist.broadcast_object(None)
+            if cmd[0] == "release":
+                return
+            if cmd[0] == "abort":
+                raise RuntimeError("rank 0 failed inside an interceptor")
+            if cmd[0] == "encode_all":
+                self._encode_all_sharded(data)
+            elif cmd[0] == "state":
+                self._engine.state_dict()
+            else:
+                raise RuntimeError(f"unknown data-parallel command {cmd!r}")
+
+    def _announce(self, *cmd):
+        if getattr(self, "_workers_serving", False):
+            self._engine.dist.broadcast_object(cmd)
+
+    def _encode_all_sharded(self, mat):
+        """encoding_prediction over ALL cells of a CellMatrix with the rows sharded contiguously
+        over the ranks (no communication in the pass itself); the (N_i, Z) float32
+        pieces are all-gathered, every rank returns the full host array."""
+        import torch
+        eng, W, r = self._engine, self._world(), self._rank()
+        N, Z = len(mat), self.encoding_size
+        per = (N + W - 1) // W
+        lo, hi = min(N, r * per), min(N, (r + 1) * per)
+        piece = torch.zeros((per, Z), dtype=torch.float32, device=eng.device)
+        if hi > lo:
+            self._encode_rows(mat, lo, hi, piece[:hi - lo])
+        full = torch.empty((W * per, Z), dtype=torch.float32, device=eng.device)
+        eng.dist.all_gather(full.view(-1), piece.view(-1))
+        return full[:N].cpu().numpy()
+
+    def _encode_rows(self, mat, lo, hi, out):
+        """E.predict on rows [lo, hi) of a device-resident CellMatrix -> out (fp32, device)."""
+        eng = self._engine
+        if eng.device.type == "cuda" and os.environ.get("CELLCOMM_B200_ENCODE_STREAM", "1") != "0":
+            rowptr, colidx, values = mat.device_csr(eng.device)
+            eng.encode_stream(rowptr, colidx, values, lo, hi, out)
+            return
+        for s in range(lo, hi, self.PREDICT_TILE):
+            m = min(self.PREDICT_TILE, hi - s)
+            eng.encode(self._stage_cells(mat, s, m), out32=out[s - lo:s - lo + m])
+
     # ------------------------------------------------------------------ checkpoint / resume
-    def save_checkpoint(self, path):
-        """Weights, RMSprop slots, BN moving statistics and RNG position -> one .npz (the
-        reference has no checkpointing)."""
-        self._require_engine().save_checkpoint(path)
+    def save_checkpoint(self, path, extra=None):
+        """Weights, RMSprop slots, BN moving statistics, the device RNG position and the host
+        RNG states -> one .npz (the reference has no checkpointing).
+        `extra`: additional scalars (e.g. the iteration number) stored as `meta/<key>`.
+        Data parallel: rank 0 writes; the other ranks take part through serve() or by calling
+        this too."""
+        eng = self._require_engine()
+        self._announce("state")
+        state = eng.state_dict()
+        state["meta/numpy_rng"] = _pack_numpy_state(np.random.get_state())
+        state["meta/prior_rng"] = np.array(json.dumps(self._prior_rng.bit_generator.state))
+        for k, v in (extra or {}).items():
+            state[f"meta/{k}"] = v
+        eng.write_checkpoint(path, state)
 
     def load_checkpoint(self, path):
-        self._require_engine().load_checkpoint(path)
+        """-> dict of the checkpoint's `meta/*` entries (e.g. {'iteration': 7})."""
+        state = self._require_engine().load_checkpoint(path)
+        if "meta/numpy_rng" in state:
+            np.random.set_state(_unpack_numpy_state(state["meta/numpy_rng"]))
+        if "meta/prior_rng" in state:
+            self._prior_rng.bit_generator.state = json.loads(str(state["meta/prior_rng"]))
+        return {k[5:]: (v.item() if getattr(v, "ndim", 1) == 0 else v)
+                for k, v in state.items() if k.startswith("meta/")}
 
     # ------------------------------------------------------------------ plumbing
     def _require_engine(self):
@@ -187,12 +316,11 @@ class ClassifyCellBiGan(BasicBiGan):
         ops.cast_f32_to_bf16(t, out)
         return out
 
-    def _tile(self, n):
-        import torch
-        buf = getattr(self, "_tile_buf", None)
+    def _tile(self, n, name="_tile_buf"):
+        buf = getattr(self, name, None)
         if buf is None or buf.shape[0] < n:
-            self._tile_buf = buf = _engine.ops.alloc2d(max(n, 1), self.gene_size,
-                                                       device=self._engine.device)
+            buf = _engine.ops.alloc2d(max(n, 1), self.gene_size, device=self._engine.device)
+            setattr(self, name, buf)
         return buf[:n]
 
     PREDICT_TILE = 4096
@@ -203,14 +331,19 @@ class ClassifyCellBiGan(BasicBiGan):
         eng = self._require_engine()
         dev = eng.device
         if role == "E":
+            if isinstance(x, CellMatrix):
+                # the encode-all-cells pass (src/intercepts/db_recorder.py:85)
+                if self._world() > 1:
+                    self._announce("encode_all")
+                    return self._encode_all_sharded(x)
+                out = torch.empty((len(x), self.encoding_size), dtype=torch.float32, device=dev)
+                self._encode_rows(x, 0, len(x), out)
+                return out.cpu().numpy()
             n = len(x)
             out = torch.empty((n, self.encoding_size), dtype=torch.float32, device=dev)
             for s in range(0, n, self.PREDICT_TILE):
                 m = min(self.PREDICT_TILE, n - s)
-                tile = self._stage_cells(x[s:s + m] if _sliceable(x) else x, s, m) \
-                    if not isinstance(x, CellBatch) else self._stage_cells(
-                        CellBatch(x.matrix, x.positions[s:s + m]))
-                eng.encode(tile, out32=out[s:s + m])
+                eng.encode(self._stage_cells(_rows(x, s, s + m)), out32=out[s:s + m])
             return out.cpu().numpy()
         enc, second = x
         z = torch.as_tensor(np.asarray(enc, dtype=np.float32)).to(dev)
@@ -226,17 +359,39 @@ class ClassifyCellBiGan(BasicBiGan):
         out = torch.empty((n, 1), dtype=torch.float32, device=dev)
         for s in range(0, n, self.PREDICT_TILE):
             m = min(self.PREDICT_TILE, n - s)
-            tile = self._stage_cells(second[s:s + m] if _sliceable(second) else second, s, m) \
-                if not isinstance(second, CellBatch) else self._stage_cells(
-                    CellBatch(second.matrix, second.positions[s:s + m]))
+            tile = self._stage_cells(second, s, m) if isinstance(second, CellMatrix) \
+                else self._stage_cells(_rows(second, s, s + m))
             eng.discriminate(z[s:s + m].contiguous(), tile, out[s:s + m])
         return out.cpu().numpy()
+
+    def evaluate_discriminator_accuracy(self, sampled_batch):
+        """(true-positives, true-negatives), reference src/bigan_basic.py:50-64 -- same draws in
+        the same order (random encodings, then the generator noise), but G.predict -> round ->
+        D.predict and E.predict -> D.predict stay on the device: the (B, genes) generated cells
+        never visit the host.  Only the two counts are read back."""
+        if self._engine is None:
+            return super().evaluate_discriminator_accuracy(sampled_batch)
+        import torch
+        eng, ops = self._engine, _engine.ops
+        n = len(sampled_batch)
+        random_encodings = self.random_encoding_vector(n)
+        noise = self.random_uniform_vector(n)           # generate_cells(encodings) draws it
+        eng.set_latents(random_encodings, noise, n)
+        fake = self._tile(n, "_fake_buf")
+        ops.round_half_even(eng.generate(n), out16=fake)
+        p = torch.empty((n, 1), dtype=torch.float32, device=eng.device)
+        eng.discriminate(eng.z32[:n], fake, p)
+        false_negatives = int(torch.count_nonzero(torch.round(p)))
+        real = self._stage_cells(sampled_batch)
+        eng.encode(real, out32=eng.gen_enc32[:n])
+        eng.discriminate(eng.gen_enc32[:n], real, p)
+        true_positives = int(torch.count_nonzero(torch.round(p)))
+        return true_positives, n - false_negatives
 
     def _train_on_batch(self, substep, x, y):
         """Model.train_on_batch of one of the compiled graphs: runs that single sub-step and
         returns its loss (the target `y` is implied by the graph, as in the reference's calls
         :144-155)."""
-        import torch
         eng = self._require_engine()
         ops = _engine.ops
         if substep in (1, 4):
@@ -255,8 +410,55 @@ class ClassifyCellBiGan(BasicBiGan):
             cells = self._stage_cells(x)
         ops.fill_f32(eng.loss_buf, 0.0)
         eng.substep(substep, cells)
-        slot = {1: 0, 2: 1, 3: 2, 4: 3, 6: 4, 8: 5}[substep]
+        slot = {1: 0, 2: 1, 3: 2, 4: 3}[substep]
         return float(eng.loss_buf[slot])
+
+    def _train_discriminator_on_batch(self, x, y):
+        """`_discriminator.train_on_batch((encodings, cells), labels)`, reference :154-155.  The
+        labels must be one constant vector (the reference only ever passes 0.95 * ones or
+        zeros, :128-129): the loss kernel takes the label as a scalar."""
+        import torch
+        eng = self._require_engine()
+        enc, cells = x
+        labels = np.asarray(y, dtype=np.float32).reshape(-1)
+        n = len(labels)
+        if len(enc) != n or len(cells) != n:
+            raise ValueError("train_on_batch: inputs and labels differ in length")
+        if n and not np.all(labels == labels[0]):
+            raise NotImplementedError("discriminator labels must be constant over the batch")
+        eng.reserve(n)
+        z = torch.as_tensor(np.asarray(enc, dtype=np.float32)).to(eng.device)
+        ops = _engine.ops
+        ops.fill_f32(eng.loss_buf, 0.0)
+        eng.gen_enc32[:n].copy_(z)
+        eng.train_discriminator(eng.gen_enc32[:n], self._stage_cells(cells), float(labels[0]), 5,
+                                eng._drop_args(8, "D", None))
+        ops.counter_add(eng.rng_counter, 1)
+        return float(eng.loss_buf[5])
+
+
+def _rows(x, lo, hi):
+    """Rows [lo, hi) of a minibatch-like object (CellBatch, DataFrame, ndarray, tensor)."""
+    if isinstance(x, CellBatch):
+        return CellBatch(x.matrix, x.positions[lo:hi])
+    if hasattr(x, "iloc"):
+        return x.iloc[lo:hi]
+    return x[lo:hi]
+
+
+def _pack_numpy_state(st):
+    """np.random.get_state() -> one uint32 array (npz-friendly, no pickle)."""
+    name, keys, pos, has_gauss, cached = st
+    assert name == "MT19937"
+    tail = np.array([pos, has_gauss], dtype=np.uint32)
+    g = np.frombuffer(np.float64(cached).tobytes(), dtype=np.uint32)
+    return np.concatenate([np.asarray(keys, dtype=np.uint32), tail, g])
+
+
+def _unpack_numpy_state(a):
+    a = np.asarray(a, dtype=np.uint32)
+    cached = float(np.frombuffer(a[626:628].tobytes(), dtype=np.float64)[0])
+    return ("MT19937", a[:624].copy(), int(a[624]), int(a[625]), cached)
 
 
 def _as_f32(a):
@@ -264,5 +466,3 @@ def _as_f32(a):
     return torch.as_tensor(np.asarray(a, dtype=np.float32))
 
 
-def _sliceable(x):
-    return not isinstance(x, (CellMatrix,))

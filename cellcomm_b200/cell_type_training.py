@@ -238,14 +238,41 @@ class CellTraining:
     def sample_cell_data(self, random_seed=None):
         return self.data.sample(self.batch_size, random_state=random_seed)
 
-    def run(self, iterations, interceptor: Callable[[int, Any], None] = None):
-        for it in range(iterations):
+    def run(self, iterations, interceptor: Callable[[int, Any], None] = None, start_iteration=0):
+        """The reference's loop (src/cell_type_training.py:40-50).  `start_iteration` (not in the
+        reference) numbers the iterations of a resumed run.
+
+        Data parallel (torchrun, one process per GPU): every rank runs this loop; each step is
+        ONE global batch of `batch_size` cells split contiguously over the ranks.  The
+        interceptor runs on rank 0 only, while the other ranks serve the collective parts of
+        what it calls (the row-sharded encode-all-cells pass, checkpoint gathers)."""
+        net = self.network
+        world = net._world() if hasattr(net, "_world") and callable(getattr(net, "_world")) else 1
+        if not isinstance(world, int):
+            world = 1                       # mocked networks
+        has_interceptor = interceptor is not None
+        if world > 1:
+            net.sync_host_rng()
+            # rank 0 decides whether the workers have interceptor work to serve
+            has_interceptor = net.broadcast_from_coordinator(has_interceptor)
+        for it in range(start_iteration, start_iteration + iterations):
             g_losses = e_losses = d_losses = 0
             for batch_it in range(self.batches_per_iteration):
                 batch = self.sample_cell_data()
-                gl, el, dl = self.network.trainings_step(batch)
+                gl, el, dl = net.trainings_step(batch)
                 g_losses += gl
                 e_losses += el
                 d_losses += dl
-            if interceptor:
-                interceptor(it, (g_losses, e_losses, d_losses))
+            if has_interceptor:
+                if world == 1:
+                    interceptor(it, (g_losses, e_losses, d_losses))
+                elif net.is_coordinator():
+                    net.begin_interceptors()
+                    try:
+                        interceptor(it, (g_losses, e_losses, d_losses))
+                    except BaseException:
+                        net.release_workers(failed=True)
+                        raise
+                    net.release_workers()
+                else:
+                    net.serve(self.data)

@@ -206,6 +206,12 @@ class _NoDist:
 
     all_reduce_grad = all_reduce
 
+    def broadcast(self, t):
+        return t
+
+    def broadcast_object(self, obj=None):
+        return obj
+
 
 class TorchDist:
     """Data-parallel plumbing over torch.distributed (NCCL over NVLink on the GPU box, gloo in
@@ -290,6 +296,22 @@ class TorchDist:
                 self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def broadcast(self, t):
+        """rank 0's tensor to every rank (start-up only)."""
+        if self.world_size > 1:
+            self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, 0)
+                                 if self.group is not None else 0, group=self.group)
+        return t
+
+    def broadcast_object(self, obj=None):
+        """rank 0's picklable object to every rank (control messages, RNG states)."""
+        box = [obj if self.rank == 0 else None]
+        if self.world_size > 1:
+            self._dist.broadcast_object_list(
+                box, src=self._dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                group=self.group)
+        return box[0]
+
     def all_reduce_grad(self, t):
         """Sum all-reduce on the gradient communicator (side-stream traffic)."""
         if self.world_size > 1:
@@ -352,6 +374,7 @@ class Net:
         self.on_grow = None
         self._gshard = None
         self._master_stale = False
+        self._slots_stale = False
         self.fuse_optimizer = False   # kernels updated inside the wgrad epilogue (1 GPU)
         self.keep_grads = False       # fused mode: also write dW (parity tests)
         self.hp, self.split = self._high_precision_tensors()
@@ -548,6 +571,7 @@ class Net:
                     L[k].copy_(a.to(self.device))
         self.ms.zero_()
         self.mom.zero_()
+        self._master_stale = self._slots_stale = False
         self.sync_compute_copy()
 
     # ------------------------------------------------------------------ precision policy
@@ -601,8 +625,10 @@ class Net:
 
     def get_slots(self):
         """RMSprop slots (ms, mom) per trainable tensor in creation order (kernel, bias | gamma,
-        beta), as host arrays: checkpointing and parity tests."""
+        beta), as host arrays: checkpointing and parity tests.  Data parallel: collective (the
+        sharded optimiser only keeps each rank's own 1/world of the slots current)."""
         self._wait_optimizer()
+        self.gather_slots()
         out = []
         for L in self.layers:
             for key in (("w32", "b32") if L["kind"] == "dense" else ("gamma", "beta")):
@@ -619,6 +645,7 @@ class Net:
                 if L[key].numel():
                     self._like(L[key], self.ms).copy_(torch.as_tensor(ms, dtype=torch.float32))
                     self._like(L[key], self.mom).copy_(torch.as_tensor(mom, dtype=torch.float32))
+        self._slots_stale = False
 
     def _like(self, view, flat):
         """The view of `flat` (ms / mom / g32) laid out like the parameter view `view` of p32."""
@@ -1073,13 +1100,13 @@ class Net:
                 self._peer_update(pr["nb"] - 1, K, self.n_flat - K, broadcast=False)
                 ops.peer_wait(self._flag_ptr(self.dist.rank, 1, 0, 0),
                               pr["nb"] * self.dist.world_size, 1, epoch_ctr=pr["ctr"], bump=True)
-                self._master_stale = True
+                self.mark_updated()
                 return
             tail = slice(K, self.n_flat)
             self.dist.all_reduce_grad(self.g32[tail])
             ops.rmsprop_step(self.p32[tail], self.p16[tail], self.g32[tail], self.ms[tail],
                              self.mom[tail], LR, RHO, MOMENTUM, EPSILON)
-            self._master_stale = True
+            self.mark_updated()
             return
         if W == 1 or not _SHARD_OPTIMIZER or K == 0 or K % (W * 256) != 0:
             self.dist.all_reduce(self.g32)
@@ -1099,20 +1126,39 @@ class Net:
         self.dist.all_reduce(self.g32[tail])
         ops.rmsprop_step(self.p32[tail], self.p16[tail], self.g32[tail], self.ms[tail],
                          self.mom[tail], LR, RHO, MOMENTUM, EPSILON)
-        self._master_stale = True
+        self.mark_updated()
+
+    def _gather_sharded(self, flat):
+        """all-gather every rank's owner shard of a flat fp32 buffer (p32 / ms / mom)"""
+        W, r = self.dist.world_size, self.dist.rank
+        if self._bucketed():
+            ranges = [(b["start"], b["end"]) for b in self.buckets]
+        else:
+            ranges = [(0, self.small_off)]
+        for a, b in ranges:
+            n = (b - a) // W
+            self.dist.all_gather(flat[a:b], flat[a + r * n:a + (r + 1) * n].clone())
+
+    def mark_updated(self):
+        """The sharded optimiser ran (possibly inside a replayed CUDA graph, where no Python
+        executes): the non-owned parts of p32 / ms / mom are stale until gathered."""
+        if self.dist.world_size > 1 and _SHARD_OPTIMIZER and not self.fuse_optimizer:
+            self._master_stale = self._slots_stale = True
 
     def gather_master(self):
-        """Make the fp32 master weights current on every rank (sharded-optimiser runs)."""
+        """Make the fp32 master weights current on every rank (sharded-optimiser runs).
+        Collective: every rank calls it."""
         if self._master_stale and self.dist.world_size > 1:
-            W, r = self.dist.world_size, self.dist.rank
-            if self._bucketed():
-                ranges = [(b["start"], b["end"]) for b in self.buckets]
-            else:
-                ranges = [(0, self.small_off)]
-            for a, b in ranges:
-                n = (b - a) // W
-                self.dist.all_gather(self.p32[a:b], self.p32[a + r * n:a + (r + 1) * n].clone())
+            self._gather_sharded(self.p32)
         self._master_stale = False
+
+    def gather_slots(self):
+        """Same for the RMSprop slots: each rank updates ms / mom only on its own shard, so a
+        checkpoint (or any reader of the slots) needs the owners' values.  Collective."""
+        if self._slots_stale and self.dist.world_size > 1:
+            self._gather_sharded(self.ms)
+            self._gather_sharded(self.mom)
+        self._slots_stale = False
 
     def _wait_optimizer(self):
         """Order the current stream after a pending side-stream update of this net."""
@@ -1235,7 +1281,11 @@ class GraphedStep:
         if idx is not None:
             self.idx.copy_(torch.as_tensor(idx), non_blocking=True)
         self.graph.replay()
-        return self.losses
+        for n in self.eng.nets.values():
+            n.mark_updated()          # no Python ran inside the graph (sharded data-parallel update)
+        # fresh device scalars: the graph's own loss tensors are overwritten by the next replay
+        # (train_on_batch returns independent floats in the reference)
+        return tuple(LossScalar(l.t.clone()) for l in self.losses)
 
 
 class BiGanEngine:
@@ -1284,6 +1334,19 @@ class BiGanEngine:
                 n.opt_stream = side
         self.loss_buf = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.rng_seed = int(torch.randint(0, 2 ** 62, (1,), generator=gen).item())
+        if self.dist.world_size > 1:
+            # replicas start from rank 0's weights and RNG key (seed=None draws a different
+            # initialisation in every process); the rank is folded into the Philox stream ids
+            # below, so every rank draws its own dropout masks / priors for its rows
+            bcast = getattr(self.dist, "broadcast", None)
+            if bcast is not None:
+                key = torch.tensor([self.rng_seed], dtype=torch.int64, device=self.device)
+                bcast(key)
+                self.rng_seed = int(key.item())
+                for n in self.nets.values():
+                    bcast(n.p32)
+                    n.sync_compute_copy()
+        self._rank_stream = (self.dist.rank & 0xFFF) << 12
         self.rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.max_batch = 0
         self.reserve(max_batch)
@@ -1318,7 +1381,7 @@ class BiGanEngine:
     def _drop_args(self, substep, net, masks):
         if masks is not None:
             return {"dropout": "masks", "masks": masks[substep][net]}
-        base = substep * 16 + {"G": 0, "E": 4, "D": 8}[net]
+        base = self._rank_stream + substep * 16 + {"G": 0, "E": 4, "D": 8}[net]
         return {"dropout": "rng", "rng": (self.rng_seed, self.rng_counter, base)}
 
     def set_latents(self, encodings, noise, rows):
@@ -1334,9 +1397,9 @@ class BiGanEngine:
         """tf.random.uniform priors on the device (src/bigan_basic.py:36-37, bigan_cont.py:52-53)."""
         self.reserve(rows)
         ops.uniform(out32=self.z32[:rows], out16=self.z16[:rows], seed=self.rng_seed,
-                    counter=self.rng_counter, stream_id=1000)
+                    counter=self.rng_counter, stream_id=self._rank_stream + 1000)
         ops.uniform(out32=self.r32[:rows], out16=self.r16[:rows], seed=self.rng_seed,
-                    counter=self.rng_counter, stream_id=1001)
+                    counter=self.rng_counter, stream_id=self._rank_stream + 1001)
 
     # ------------------------------------------------------------------ the step
     def train_step(self, x16, masks=None):
@@ -1404,12 +1467,7 @@ class BiGanEngine:
             ops.round_half_even(gen, out16=cells)
         elif k == 6:
             # _discriminator.train_on_batch((encodings, generated_cells), y_zeros)   :137
-            logit = D.forward({"z": z, "cell": cells}, B, bn_train=True, pre_activation=True,
-                              **self._drop_args(6, "D", masks))
-            dz1 = D.output_grad(B)
-            ops.bce_fwd_bwd(logit, 0.0, n_total, L[4:5], dz1)
-            D.backward(dz1, train=True)
-            D.apply_rmsprop()
+            self.train_discriminator(z, cells, 0.0, 4, self._drop_args(6, "D", masks))
         elif k == 7:
             # generated_encodings = trainings_encoding_prediction(batch)            :138
             self.encode(x16, out32=self.gen_enc32[:B])
@@ -1417,14 +1475,24 @@ class BiGanEngine:
                 ops.argmax_onehot(self.gen_enc32[:B], out32=self.gen_enc32[:B])
         elif k == 8:
             # _discriminator.train_on_batch((generated_encodings, batch), y_ones)    :139
-            logit = D.forward({"z": self.gen_enc32[:B], "cell": x16}, B, bn_train=True,
-                              pre_activation=True, **self._drop_args(8, "D", masks))
-            dz1 = D.output_grad(B)
-            ops.bce_fwd_bwd(logit, REAL_LABEL, n_total, L[5:6], dz1)
-            D.backward(dz1, train=True)
-            D.apply_rmsprop()
+            self.train_discriminator(self.gen_enc32[:B], x16, REAL_LABEL, 5,
+                                     self._drop_args(8, "D", masks))
         else:
             raise ValueError(f"no sub-step {k}")
+
+    def train_discriminator(self, z, cells, label, loss_slot, drop_args):
+        """One `_discriminator.train_on_batch((z, cells), label * ones)`: BCE on D's sigmoid
+        output against a constant label vector, backward, RMSprop on D
+        (src/bigan_classify.py:112-115,154-155).  z: [B, Z] fp32, cells: [B, genes] bf16."""
+        B = cells.shape[0]
+        D = self.D
+        logit = D.forward({"z": z, "cell": cells}, B, bn_train=True, pre_activation=True,
+                          **drop_args)
+        dz1 = D.output_grad(B)
+        ops.bce_fwd_bwd(logit, float(label), B * self.dist.world_size,
+                        self.loss_buf[loss_slot:loss_slot + 1], dz1)
+        D.backward(dz1, train=True)
+        D.apply_rmsprop()
 
     def snapshot_state(self):
         """Device copies of everything a training step mutates (weights, bf16 copies, RMSprop
@@ -1487,20 +1555,26 @@ class BiGanEngine:
         self.rng_counter.fill_(int(state["meta/rng_counter"]))
         self._graphs.clear()          # captured steps baked the old RNG seed in
 
-    def save_checkpoint(self, path):
-        """One .npz file (written atomically).  Data-parallel runs: call on every rank (the
-        sharded fp32 master weights are gathered collectively); rank 0 writes."""
+    def write_checkpoint(self, path, state):
+        """rank 0 writes `state` (a state_dict(), possibly with extra meta entries) atomically."""
         import numpy as np
-        state = self.state_dict()
         if self.dist.rank == 0:
             tmp = path + ".tmp.npz"
             np.savez(tmp, **state)
             os.replace(tmp, path)
 
+    def save_checkpoint(self, path):
+        """One .npz file (written atomically).  Data-parallel runs: call on every rank (the
+        sharded fp32 master weights and RMSprop slots are gathered collectively); rank 0 writes."""
+        self.write_checkpoint(path, self.state_dict())
+
     def load_checkpoint(self, path):
+        """-> the loaded state (callers read their own `meta/*` entries from it)."""
         import numpy as np
         with np.load(path, allow_pickle=False) as f:
-            self.load_state_dict({k: f[k] for k in f.files})
+            state = {k: f[k] for k in f.files}
+        self.load_state_dict(state)
+        return state
 
     def join(self):
         """Order the current stream after every pending side-stream optimiser update (call
@@ -1560,6 +1634,128 @@ class BiGanEngine:
         """E.predict on a [rows, gene_size] bf16 tile; fp32 result in out32 when given."""
         return self.E.forward({"cell": x16}, x16.shape[0], bn_train=False, dropout="off",
                               out32=out32)
+
+    ENCODE_TILE = 4096
+
+    def encode_plan(self, tile_rows=None):
+        """cc_encode_plan for this engine's encoder: the op list Net.forward(bn_train=False,
+        dropout="off") would launch for one tile (same kernels, same precision policy), over
+        scratch slots.  None when a layer has width 0 (the 5-gene fixture's Dense(0))."""
+        from . import _lib
+        tile_rows = int(tile_rows or self.ENCODE_TILE)
+        cached = getattr(self, "_enc_plan", None)
+        if cached is not None and cached[0] == tile_rows:
+            return cached[1]
+        net, g = self.E, self.E.g
+        if any(w == 0 for w in g.widths):
+            return None
+        plan = _lib.EncodePlan()
+        slots = []                      # (width, fp32)
+
+        def new_slot(width, fp32):
+            slots.append((int(width), int(bool(fp32))))
+            return len(slots) - 1
+
+        cell = g.inputs["cell"]
+        val = {cell: new_slot(g.widths[cell], False)}      # tensor id -> slot
+        operands = {}                                       # tensor id -> [bf16 slots]
+        ops_ = []
+
+        def emit(**kw):
+            op = plan.ops[len(ops_)]
+            for k, v in kw.items():
+                setattr(op, k, v)
+            ops_.append(op)
+            return op
+
+        def gemm_operands(t):
+            if t not in operands:
+                s_ = val[t]
+                if not slots[s_][1]:
+                    operands[t] = [s_]
+                elif t in net.split:
+                    hi, lo = new_slot(g.widths[t], False), new_slot(g.widths[t], False)
+                    op = emit(kind=_lib.ENC_SPLIT, n_in=1, out=hi, out2=lo)
+                    op.in_[0] = s_
+                    operands[t] = [hi, lo]
+                else:
+                    sh = new_slot(g.widths[t], False)
+                    op = emit(kind=_lib.ENC_COPY, n_in=1, out=sh)
+                    op.in_[0] = s_
+                    operands[t] = [sh]
+            return operands[t]
+
+        last = g.nodes[-1]
+        for node in g.nodes:
+            kind, out = node["kind"], node["out"]
+            if kind == "dense":
+                L = net.layers[node["layer"]]
+                segs, ro = [], 0
+                for i in node["ins"]:
+                    for term in gemm_operands(i):
+                        segs.append((term, ro))
+                    ro += g.widths[i]
+                if len(segs) > 4:
+                    return None
+                is_last = node is last
+                fp32 = out in net.hp
+                dst = -1 if (is_last and fp32) else new_slot(g.widths[out], fp32)
+                op = emit(kind=_lib.ENC_DENSE, n_in=len(segs), out=dst, width=L["N"],
+                          act=_ACT[node["act"]], w16=L["w16"].data_ptr(), ldw=L["ld"],
+                          bias=L["b32"].data_ptr())
+                for j, (sl, r_) in enumerate(segs):
+                    op.in_[j], op.w_row[j] = sl, r_
+                if is_last and not fp32:
+                    op2 = emit(kind=_lib.ENC_COPY, n_in=1, out=-1)
+                    op2.in_[0] = dst
+                val[out] = dst
+            elif kind == "bn":
+                L = net.layers[node["layer"]]
+                dst = new_slot(g.widths[out], out in net.hp)
+                op = emit(kind=_lib.ENC_BN_INFER, n_in=1, out=dst, gamma=L["gamma"].data_ptr(),
+                          beta=L["beta"].data_ptr(), mean=L["moving_mean"].data_ptr(),
+                          var=L["moving_var"].data_ptr(), eps=BN_EPS)
+                op.in_[0] = val[node["ins"][0]]
+                val[out] = dst
+            elif kind == "dropout":
+                val[out] = val[node["ins"][0]]           # predict: Dropout is the identity
+            elif kind == "softmax":
+                dst = new_slot(g.widths[out], out in net.hp)
+                op = emit(kind=_lib.ENC_SOFTMAX, n_in=1, out=dst)
+                op.in_[0] = val[node["ins"][0]]
+                val[out] = dst
+            else:                                        # the encoders have no Concatenate node
+                return None
+            if len(ops_) > _lib.ENC_MAX_OPS - 2 or len(slots) > _lib.ENC_MAX_SLOTS - 3:
+                return None
+        plan.n_cols, plan.tile_rows = self.Gn, tile_rows
+        plan.n_slots, plan.n_ops = len(slots), len(ops_)
+        for i, (w, f) in enumerate(slots):
+            plan.slot_width[i], plan.slot_fp32[i] = w, f
+        nbytes = ops.encode_scratch_bytes(plan)
+        scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        ws = ops.workspace(self.device)
+        plan.scratch, plan.scratch_bytes = scratch.data_ptr(), nbytes
+        plan.workspace, plan.workspace_elems = ws.data_ptr(), ws.numel()
+        self._enc_plan = (tile_rows, plan, scratch)
+        return plan
+
+    def encode_stream(self, rowptr, colidx, values, row_begin, row_end, out32, tile_rows=None):
+        """encoding_prediction for rows [row_begin, row_end) of a device CSR in ONE C call
+        (cc_encode_stream): gather + encoder forward per tile, no Python between tiles.  Falls
+        back to the tile loop over encode() for encoders the plan cannot express."""
+        self.E._wait_optimizer()
+        plan = self.encode_plan(tile_rows)
+        if plan is None:
+            tile = int(tile_rows or self.ENCODE_TILE)
+            buf = ops.alloc2d(min(tile, max(1, row_end - row_begin)), self.Gn, device=self.device)
+            for s in range(row_begin, row_end, tile):
+                m = min(tile, row_end - s)
+                ops.gather_rows(rowptr, colidx, values, self.Gn, row_start=s, n_rows=m,
+                                out16=buf[:m])
+                self.encode(buf[:m], out32=out32[s - row_begin:s - row_begin + m])
+            return
+        ops.encode_stream(rowptr, colidx, values, row_begin, row_end, plan, out32)
 
     def generate(self, rows, out32=None):
         """G.predict on the staged latents (first `rows`)."""

@@ -47,25 +47,29 @@ def load_encodings(log_dir, iteration):
 class Checkpoints:
     """Interceptor that saves `network.save_checkpoint()` every `every` iterations to
     `<log_dir>/checkpoint.npz` (atomic replace), and `resume(trainer)` that restores the newest
-    one before a run.  The reference persists nothing but encodings and loss CSVs (SURVEY.md 5);
-    this is row f4 of its "next" list wired into the interceptor mechanism."""
+    one before a run.  The checkpoint also holds the iteration number and the host RNG states
+    (numpy's global state = batch sampler, and the private prior generator), so
+    `trainer.run(n, interceptor, start_iteration=ck.resume(trainer))` continues the
+    interrupted run: same batches, same priors, iteration numbers that do not collide with the
+    recorder's.  The reference persists nothing but encodings and loss CSVs; this
+    is row f4 of its "next" list wired into the interceptor mechanism."""
 
     def __init__(self, log_dir, every=1):
         self.path = os.path.join(log_dir, 'checkpoint.npz')
         self.every = max(1, int(every))
 
     def resume(self, trainer):
-        """-> True when a checkpoint was found and loaded."""
+        """-> the iteration to continue with (0 when there is no checkpoint; truthy otherwise)."""
         if not os.path.exists(self.path):
-            return False
-        trainer.network.load_checkpoint(self.path)
-        return True
+            return 0
+        meta = trainer.network.load_checkpoint(self.path) or {}
+        return int(meta.get('iteration', -1)) + 1
 
     def create_interceptor(self, trainer):
         os.makedirs(os.path.dirname(self.path) or '.', exist_ok=True)
 
         def intercept(it, _):
             if (it + 1) % self.every == 0:
-                trainer.network.save_checkpoint(self.path)
+                trainer.network.save_checkpoint(self.path, extra={'iteration': it})
 
         return intercept

@@ -75,6 +75,8 @@ class LayerView:
 
     def get_weights(self):
         net = self._model._net()
+        net._wait_optimizer()
+        net.gather_master()      # data parallel: collective, like NetModel.get_weights
         L = net.layers[self._index]
         keys = ("w32", "b32") if L["kind"] == "dense" else (
             "gamma", "beta", "moving_mean", "moving_var")
@@ -172,6 +174,15 @@ class NetModel:
         reference's deep copy of every layer (src/bigan_basic.py:72-81)."""
         p = self._net().p32
         return np.array([float(p.sum()), float((p * p).sum())])
+
+    def train_on_batch(self, x, y=None):
+        """Model.train_on_batch of a compiled component.  Only the discriminator is compiled on
+        its own in the reference (src/bigan_classify.py:112-115); G and E are trained through
+        the four combined graphs (`_train_gen_w_discr` ...)."""
+        if self.role != "D" or not self._is_compiled:
+            raise RuntimeError(f"{self.name} is not compiled for training on its own; use the "
+                               f"BiGAN's combined training graphs")
+        return self._owner._train_discriminator_on_batch(x, y)
 
     def predict(self, x, **_kwargs):
         """Model.predict: inference mode (BN moving stats, dropout off), float32 host result.

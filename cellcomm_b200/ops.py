@@ -186,6 +186,24 @@ def gather_rows(rowptr, colidx, values, n_cols, *, row_idx=None, row_start=0, n_
                              _p(out32), _ld(out32), _stream()))
 
 
+def encode_scratch_bytes(plan):
+    return int(_lib.load().cc_encode_scratch_bytes(C.byref(plan)))
+
+
+def encode_stream(rowptr, colidx, values, row_begin, row_end, plan, out32):
+    """The encode-all-cells pass over CSR rows [row_begin, row_end) in one C call
+    (cc_encode_stream); plan: _lib.EncodePlan built by BiGanEngine.encode_plan()."""
+    _req(rowptr, torch.int64, "rowptr")
+    _req(colidx, torch.int32, "colidx")
+    _req(values, torch.float32, "values")
+    _req(out32, torch.float32, "out32")
+    if out32.shape[0] != row_end - row_begin:
+        raise ValueError("encode_stream: out32 must have one row per encoded cell")
+    check(_lib.load().cc_encode_stream(rowptr.data_ptr(), colidx.data_ptr(), values.data_ptr(),
+                                       int(row_begin), int(row_end), C.byref(plan),
+                                       out32.data_ptr(), _ld(out32), _stream()))
+
+
 # --------------------------------------------------------------------------- tail kernels
 def _act_t(t, name):
     """bf16-or-fp32 activation operand"""

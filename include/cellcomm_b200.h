@@ -391,6 +391,60 @@ int cc_bias_act(const float* bias, int32_t act, void* out16, int64_t ld16, float
 /* fp32 scalar helpers */
 int cc_fill_f32(float* dst, float value, int64_t n, cc_stream_t stream);
 
+/* ------------------------------------------------ encode-all-cells pass (one call)
+ * replaces: BasicBiGan.encoding_prediction(trainer.data) = encoder.predict(all cells)
+ *   src/bigan_basic.py:29-30, called from src/intercepts/db_recorder.py:85 (and the
+ *   plot / .enc interceptors): Keras runs it 32 rows at a time on the dense DataFrame.
+ * Here: for every tile of `tile_rows` cells of rows [row_begin, row_end) of the device CSR --
+ * cc_gather_rows into slot 0, then the encoder's layers in inference mode as the op list below
+ * -- enqueued on `stream` from this one call.  out32: [row_end - row_begin, Z] fp32, leading
+ * dimension ld_out.  Rows shard over GPUs by giving each rank its own [row_begin, row_end).
+ *
+ * The encoder is a small program over scratch slots (slot 0 = the gathered bf16 cell tile,
+ * slot -1 = the output tile): the caller derives it from its layer graph, so both reference
+ * encoders (src/bigan_cont.py:28-41, src/bigan_classify.py:28-40) run through the same entry
+ * point.  Slot s is a [tile_rows, pad64(slot_width[s])] bf16 (or fp32) tile carved out of
+ * `scratch` (zero-initialised by the caller once; cc_encode_scratch_bytes gives its size). */
+#define CC_ENC_MAX_OPS 32
+#define CC_ENC_MAX_SLOTS 32
+enum {
+  CC_ENC_DENSE = 0,    /* out = act(sum_s in[s] @ w16[w_row[s] : w_row[s]+width(in[s]), :] + bias) */
+  CC_ENC_SPLIT = 1,    /* fp32 in[0] -> bf16 hi (out) + lo (out2): two-term GEMM operand */
+  CC_ENC_COPY = 2,     /* out = in[0] (dtype cast as the slots say) */
+  CC_ENC_BN_INFER = 3, /* BatchNormalization on the moving statistics */
+  CC_ENC_SOFTMAX = 4   /* out = softmax(in[0]); the fp32 result also goes to the output tile */
+};
+typedef struct cc_enc_op {
+  int32_t kind;
+  int32_t n_in;
+  int32_t in[CC_GEMM_MAX_SEG];
+  int32_t w_row[CC_GEMM_MAX_SEG]; /* DENSE: first kernel row of each input segment */
+  int32_t out, out2;
+  int32_t width;                  /* DENSE: output width N */
+  int32_t act;                    /* DENSE: cc_act */
+  const void* w16;                /* DENSE: bf16 kernel [K_total, width], leading dimension ldw */
+  int64_t ldw;
+  const float* bias;
+  const float *gamma, *beta, *mean, *var; /* BN_INFER */
+  float eps;
+} cc_enc_op;
+typedef struct cc_encode_plan {
+  int32_t n_cols;    /* gene_size */
+  int32_t tile_rows; /* cells per tile */
+  int32_t n_slots, n_ops;
+  int32_t slot_width[CC_ENC_MAX_SLOTS];
+  int32_t slot_fp32[CC_ENC_MAX_SLOTS];
+  cc_enc_op ops[CC_ENC_MAX_OPS];
+  void* scratch;
+  int64_t scratch_bytes;
+  float* workspace; /* split-K scratch for cc_gemm (may be NULL) */
+  int64_t workspace_elems;
+} cc_encode_plan;
+int64_t cc_encode_scratch_bytes(const cc_encode_plan* plan);
+int cc_encode_stream(const int64_t* rowptr_dev, const int32_t* colidx_dev, const float* values_dev,
+                     int64_t row_begin, int64_t row_end, const cc_encode_plan* plan, float* out32,
+                     int64_t ld_out, cc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

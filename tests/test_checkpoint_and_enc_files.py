@@ -129,12 +129,14 @@ class _CkptNet:
     def __init__(self):
         self.saved, self.loaded = [], []
 
-    def save_checkpoint(self, path):
+    def save_checkpoint(self, path, extra=None):
         self.saved.append(path)
+        self.extra = extra
         open(path, "wb").write(b"x")
 
     def load_checkpoint(self, path):
         self.loaded.append(path)
+        return dict(self.extra)
 
 
 def test_checkpoint_interceptor_saves_every_n_and_resumes(tmp_path):
@@ -144,9 +146,10 @@ def test_checkpoint_interceptor_saves_every_n_and_resumes(tmp_path):
         network = _CkptNet()
 
     ck = Checkpoints(str(tmp_path / "logs" / "r"), every=2)
-    assert ck.resume(T) is False and T.network.loaded == []
+    assert ck.resume(T) == 0 and T.network.loaded == []
     intercept = ck.create_interceptor(T)
     for it in range(5):
         intercept(it, (0.0, 0.0, 0.0))
     assert len(T.network.saved) == 2 and T.network.saved[0].endswith("checkpoint.npz")   # it 1, 3
-    assert ck.resume(T) is True and T.network.loaded == [ck.path]
+    # the newest checkpoint was written at iteration 3: the resumed run continues with 4
+    assert ck.resume(T) == 4 and T.network.loaded == [ck.path]
