@@ -190,13 +190,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def oracle_step_rate(batch, steps, warmup, genes, note, variant="cont"):
+def oracle_step_rate(batch, steps, warmup, genes, note, variant="cont", model=None):
     """cells/s of the oracle's trainings_step on the host cores (all threads)."""
     import torch
     from oracle import bigan_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     Z = Z_CLASSIFY if variant == "classify" else 3
-    m = O.OracleBiGan(variant, Z, genes, seed=0)
+    m = model if model is not None else O.OracleBiGan(variant, Z, genes, seed=0)
     g = torch.Generator().manual_seed(0)
     x = (torch.rand(batch, genes, generator=g) < 0.06).float() * \
         (torch.poisson(torch.full((batch, genes), 1.2), generator=g) + 1)
@@ -219,26 +219,51 @@ def oracle_step_rate(batch, steps, warmup, genes, note, variant="cont"):
             "sec_per_step": dt}
 
 
+def pick_sample_batch(batch, steps, genes, variant, budget_s, model=None):
+    """The largest sample of the workload batch (batch, 1024, 512, 256, 128 cells) whose
+    `steps` oracle steps fit the time budget, from one probe step at 128 cells (the oracle's
+    time per step is affine in the batch: GEMMs scale with it, the optimiser sweep does not)."""
+    probe = oracle_step_rate(min(128, batch), 1, 1, genes, "probe", variant, model)["sec_per_step"]
+    for cand in (batch, 1024, 512, 256, 128):
+        if cand <= batch and probe * max(1.0, cand / 128.0) * steps <= budget_s:
+            return cand, probe
+    return min(128, batch), probe
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  TensorFlow/Keras is
     not installed and cannot be (no network), so this times the oracle port on the host cores,
-    rank 0 only."""
+    rank 0 only.  Same `config` as the GPU arm (same matrix shape, networks and per-GPU batch);
+    each timed step is a BOUNDED SAMPLE of that batch -- the largest of {batch, 1024, 512, 256,
+    128} cells that keeps the whole run within --ref-budget seconds -- and the metric is the
+    same cells/s.  (The oracle's cells/s grows slowly with the sample: its GEMMs are compute
+    bound on the CPU at every one of these sizes and the batch-independent optimiser sweep is
+    a few percent of a step.)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.ref_batch
     if args.workload == "encode":
         return run_reference_encode(args)
-    res = oracle_step_rate(batch, max(1, args.steps), max(0, args.warmup), args.genes,
-                           "same synthetic count model as the GPU arm",
-                           "classify" if args.workload == "classify" else "cont")
+    variant = "classify" if args.workload == "classify" else "cont"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    from oracle import bigan_oracle as O
+    model = O.OracleBiGan(variant, Z_CLASSIFY if variant == "classify" else 3, args.genes, seed=0)
+    if args.ref_batch > 0:
+        sample, probe = args.ref_batch, None
+    else:
+        sample, probe = pick_sample_batch(args.batch, steps + warmup, args.genes, variant,
+                                          args.ref_budget, model)
+    res = oracle_step_rate(sample, steps, warmup, args.genes,
+                           f"a {sample}-cell sample of the GPU arm's {args.batch}-cell batch per "
+                           f"step, same synthetic count model", variant, model)
     line = {
         "impl": "reference", "metric": "BiGAN train cells/sec", "value": res["value"],
         "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": res["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, batch),
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": workload_config(args, args.batch),
+        "cpu_baseline": dict({k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                             sample_cells_per_step=sample, probe_sec_per_128_cells=probe),
         "e2e": {"value": res["value"], "unit": "cells/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -272,7 +297,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         init_distributed(dev)
-    B = args.batch
+    # weak scaling (default): --batch cells per GPU; --strong: --batch is the global batch
+    B = args.batch // world if args.strong else args.batch
+    assert B >= 1 and (not args.strong or B * world == args.batch), "--strong: batch % gpus != 0"
 
     def barrier():
         if world > 1:
@@ -289,25 +316,27 @@ def run_ours(args):
     t_setup = time.time()
     data = make_matrix(args.cells, args.genes, 20260101, dev)
     assert data.shape == (args.cells, args.genes)
-    np.random.seed(1000 + rank)          # each rank samples its own cells (weak scaling)
     classify = args.workload == "classify"
     Z = Z_CLASSIFY if classify else 3
+    # the public API takes the GLOBAL batch: every rank draws the same permutation(N)[:B*world]
+    # and trains on its contiguous B rows (CellTraining.run / trainings_step)
     if classify:
         from cellcomm_b200.bigan_classify import ClassifyCellBiGan
         trainer = CellTraining.__new__(CellTraining)     # the reference's trainer builds the
-        trainer.batch_size, trainer.data = B, data         # Continuous variant only
+        trainer.batch_size, trainer.data = B * world, data   # Continuous variant only
         trainer.batches_per_iteration = 10
         trainer.network = ClassifyCellBiGan(Z, gene_size=args.genes)
     else:
-        trainer = CellTraining(data, batch_size=B, encoding_size=Z)
+        trainer = CellTraining(data, batch_size=B * world, encoding_size=Z)
     net = trainer.network
     e = net._engine
     rowptr, colidx, values = data.device_csr(dev)
     setup_s = time.time() - t_setup
 
-    # ---- device-resident loop: indices + priors already in HBM
+    # ---- device-resident loop: indices + priors already in HBM (each rank its own rows)
     n_pre = args.warmup + args.steps
-    idx_all = torch.stack([torch.from_numpy(np.random.permutation(args.cells)[:B])
+    rs = np.random.RandomState(1000 + rank)
+    idx_all = torch.stack([torch.from_numpy(rs.permutation(args.cells)[:B])
                            for _ in range(n_pre)]).to(dev)
     x16 = ops.alloc2d(B, args.genes, device=dev)
     e.reserve(B)
@@ -386,14 +415,31 @@ def run_ours(args):
         ev1.record()
         barrier()
         ms_small = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        # ... and end to end through the public API at that batch (host sampling, H2D of the
+        # indices + priors, three loss floats read back per step)
+        for _ in range(2):
+            [float(v) for v in net.trainings_step(data.sample(Bs))]
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            _ = [float(v) for v in net.trainings_step(data.sample(Bs))]
+        e.join()
+        ev1.record()
+        barrier()
+        ms_small_e2e = ev0.elapsed_time(ev1) / args.steps
         small = {"batch_per_gpu": Bs, "value": Bs * world / (ms_small / 1e3), "unit": "cells/s",
                  "ms_per_step": ms_small,
+                 "e2e": {"value": Bs / (ms_small_e2e / 1e3), "unit": "cells/s",
+                         "ms_per_step": ms_small_e2e, "h2d_bytes_per_step": Bs * 8 + 2 * Bs * 3 * 4,
+                         "d2h_bytes_per_step": 12},
                  "note": "reference default batch; the step streams every weight and optimiser "
                          "slot once per update (26 B/parameter), so it is HBM-bound: "
                          f"{1.843e9 * 26 / 1e9:.1f} GB per step at the measured HBM peak = "
                          f"{1.843e9 * 26 / (peaks()['hbm_gbs'] * 1e9) * 1e3:.1f} ms"}
 
     # ---- end to end through the public API (host sampling, H2D indices+priors, D2H losses)
+    np.random.seed(1000)
+    net.sync_host_rng()           # data parallel: one global batch / prior stream on all ranks
     for _ in range(min(2, args.warmup)):
         [float(v) for v in net.trainings_step(trainer.sample_cell_data())]
     barrier()
@@ -465,10 +511,9 @@ def run_ours(args):
     barrier()
     ms_enc = max_over_ranks(ev0.elapsed_time(ev1)) / args.encode_reps
     def encode_e2e():
-        if world == 1:
-            return net.encoding_prediction(data)      # the DbRecorder's call, float32 host array
-        encode_shard()
-        return enc_out.cpu()
+        # the DbRecorder's call, float32 host array; data parallel: rows sharded over the ranks,
+        # (N_i, Z) pieces all-gathered (collective: every rank calls it)
+        return net.encoding_prediction(data)
 
     encode_e2e()
     barrier()
@@ -580,7 +625,8 @@ def run_ours(args):
     line = {
         "metric": "BiGAN train cells/sec", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+        "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(args, B),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": "cells/s",
@@ -640,10 +686,130 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in oracle_step_rate(
-            args.ref_batch, 3, 1, args.genes, "1 warm-up + 3 timed steps",
+            args.small_batch or 128, 3, 1, args.genes, "1 warm-up + 3 timed steps",
             "classify" if classify else "cont").items()
             if k != "sec_per_step"}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------ train + record
+def run_record(args):
+    """BASELINE.json configs[2]: ContinuousCellBiGan training with the per-iteration
+    encode-all-cells pass feeding `DbRecorder.intercept`, data parallel, through the product
+    entry point `CellTraining.run` (what `python3 src` / `torchrun -m cellcomm_b200` executes;
+    reference src/__main__.py:44-66, src/cell_type_training.py:40-50,
+    src/intercepts/db_recorder.py:82-108).
+
+    One "step" = one ITERATION of the reference loop: 10 `trainings_step`s on global batches of
+    batch x gpus cells, then the interceptor on rank 0 -- encode all cells (rows sharded over
+    the ranks), x255, duplicate groups, one `encits` document into the in-memory Mongo."""
+    import tempfile
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cellcomm_b200 import intercepts, ops
+    from cellcomm_b200.cell_type_training import CellTraining
+    from cellcomm_b200.intercepts import db_recorder as dbr
+    from cellcomm_b200.intercepts.fake_mongo import MongoClient as FakeMongo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        init_distributed(dev)
+    B = args.batch // world if args.strong else args.batch
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    data = make_matrix(args.cells, args.genes, 20260101, dev)
+    np.random.seed(1000)
+    trainer = CellTraining(data, batch_size=B * world, encoding_size=Z)
+    net, bpi = trainer.network, trainer.batches_per_iteration
+    icpt, spent = None, {"s": 0.0}
+    if rank == 0:
+        tmp = tempfile.mkdtemp(prefix="cellcomm_record_")
+        src = {}
+        for kind in dbr.SOURCE_KINDS:
+            src[kind] = os.path.join(tmp, f"synthetic_{kind}.{'mtx' if kind == 'matrix' else 'tsv'}")
+            open(src[kind], "w").close()
+        FakeMongo(dbr.MONGO_URL).drop_database(dbr.MONGO_DB)
+        rec = dbr.DbRecorder("bench-record", src, client_factory=FakeMongo)
+        rec.store_encoding_run()
+        rec.barcodes = [f"CELL{i:07d}-1" for i in range(args.cells)]   # (cells imported before)
+        rec.cell_ids = list(range(1, args.cells + 1))
+        record = rec.create_interceptor(trainer)
+
+        def icpt(it, losses):
+            t0 = time.perf_counter()
+            _ = [float(v) for v in losses]
+            record(it, losses)
+            spent["s"] += time.perf_counter() - t0
+
+    it = 0
+    for _ in range(max(1, min(args.warmup, 2))):
+        trainer.run(1, icpt, start_iteration=it)
+        it += 1
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    spent["s"] = 0.0
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        trainer.run(1, icpt, start_iteration=it)
+        it += 1
+    net._engine.join()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = ops.launch_count() - l0
+    gs = [g for g in net._engine._graphs.values()]
+    if gs:
+        launches += gs[0].launches_per_replay * bpi * args.steps
+    if rank == 0:
+        clock_info = clocks.stop()
+        docs = FakeMongo(dbr.MONGO_URL)[dbr.MONGO_DB][dbr.ITERATIONS_COLLECTION].find(
+            {"eid": "bench-record"}, {"_id": 0, "it": 1})
+        cells_per_step = B * world * bpi
+        value = cells_per_step * args.steps / (ms / 1e3)
+        cfg = workload_config(args, B)
+        cfg["workload"] = (f"ContinuousCellBiGan CellTraining.run: {bpi} trainings_steps + "
+                           f"encode-all-cells + DbRecorder.intercept per iteration, "
+                           f"{args.cells} cells x {args.genes} genes (BASELINE.json configs[2])")
+        line = {
+            "metric": "BiGAN train cells/sec", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "clocks": clock_info, "gpu_launches": int(launches),
+            "e2e": {"value": value, "unit": "cells/s",
+                    "h2d_bytes_per_step": bpi * (B * 8 + 2 * B * world * Z * 4),
+                    "d2h_bytes_per_step": bpi * 12 + args.cells * Z * 4,
+                    "path": "CellTraining.run(1, DbRecorder interceptor): the whole timed region "
+                            "IS the public API (host sampling, index/prior uploads, losses and "
+                            "all encodings read back, documents built and stored)"},
+            "record": {"iterations_recorded": len(docs), "cells_encoded_per_iteration": args.cells,
+                       "interceptor_seconds_per_iteration": spent["s"] / args.steps,
+                       "interceptor_share_of_step": spent["s"] * 1e3 / ms,
+                       "store": "in-memory Mongo stand-in (mongod / pymongo are not in the image)"},
+            "roofline": None, "cpu_baseline": None,
+            "note": "configs[2] composite; the kernel rooflines are reported by the train and "
+                    "encode workloads",
+        }
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -872,14 +1038,18 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("CELLCOMM_BENCH_BATCH", "2048")),
                     help="cells per GPU per trainings_step (reference default 128; 2048 saturates "
                          "the tensor cores)")
-    ap.add_argument("--ref-batch", type=int, default=128,
+    ap.add_argument("--ref-budget", type=float, default=240.0,
+                    help="--impl reference: seconds of oracle work the whole run may take")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch is the GLOBAL batch, split over the GPUs")
+    ap.add_argument("--ref-batch", type=int, default=0,
                     help="batch of the CPU arm's bounded sample (the reference's default)")
     ap.add_argument("--cells", type=int, default=CELLS)
     ap.add_argument("--genes", type=int, default=GENES)
     ap.add_argument("--encode-tile", type=int, default=4096)
     ap.add_argument("--encode-reps", type=int, default=2)
     ap.add_argument("--loader-cells", type=int, default=2000)
-    ap.add_argument("--workload", default="train", choices=["train", "classify", "encode", "loader"],
+    ap.add_argument("--workload", default="train", choices=["train", "classify", "encode", "loader", "record"],
                     help="train: ContinuousCellBiGan trainings_step (BASELINE configs[1], the "
                          "headline); classify: ClassifyCellBiGan (configs[3]); encode: the "
                          "encode-only pass over --encode-cells cells (configs[4]); loader: "
@@ -902,6 +1072,8 @@ def main():
         run_reference(args)
     elif args.workload == "encode":
         run_encode(args)
+    elif args.workload == "record":
+        run_record(args)
     else:
         run_ours(args)
 

@@ -452,6 +452,11 @@ class OracleBiGan:
             out.append((ms.clone(), mom.clone()))
         return out
 
+    def set_slots(self, net, slots):
+        """[(ms, mom)] per trainable tensor, creation order (the inverse of get_slots)."""
+        for p, (ms, mom) in zip(trainable_params(self.nets()[net]), slots):
+            self.slots[id(p)] = (self.t(ms).clone(), self.t(mom).clone())
+
     def set_weights(self, net, arrays):
         it = iter(arrays)
         for l in self.nets()[net]:
