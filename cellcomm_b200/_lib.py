@@ -48,6 +48,8 @@ class PeerRmspropDesc(C.Structure):
         ("ready", vp), ("epoch", c_u32),
         ("epoch_ctr", vp),
         ("p16_multicast", vp),
+        ("p16lo", vp * 16), ("p16lo_multicast", vp),
+        ("lo_begin", c_i64 * 2), ("lo_end", c_i64 * 2),
     ]
 
 

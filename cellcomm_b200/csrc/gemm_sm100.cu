@@ -853,6 +853,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   }
 }
 
+}  // namespace cc
+#include "wgrad_rmsprop_kernel.cuh"
+namespace cc {
+
 // Sum split-K partials and apply the epilogue.  One thread per (row, 32-col chunk).
 __global__ void splitk_finalize_kernel(const EpiParams e, const float* __restrict__ partial,
                                        long long partial_ld, long long partial_stride, int splits) {
@@ -902,9 +906,10 @@ struct MapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
   uint32_t box_inner, box_outer;
+  uint32_t kind;  // element type / swizzle / L2 promotion
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld &&
-           box_inner == o.box_inner && box_outer == o.box_outer;
+           box_inner == o.box_inner && box_outer == o.box_outer && kind == o.kind;
   }
 };
 struct MapKeyHash {
@@ -914,16 +919,23 @@ struct MapKeyHash {
     h ^= k.outer + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= k.ld + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= ((uint64_t)k.box_inner << 32 | k.box_outer) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.kind + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     return (size_t)h;
   }
 };
 
-// bf16 row-major [outer, inner] tensor with leading dimension ld (elements).
-static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                    uint32_t box_inner, uint32_t box_outer) {
+enum MapKind : uint32_t {
+  MAP_BF16_SW128 = 0,   // GEMM operands
+  MAP_F32_SW128 = 1,    // optimiser state blocks (32 fp32 = one 128-byte swizzle row)
+  MAP_BF16_SW64 = 2     // bf16 weight copy blocks (32 bf16 = one 64-byte swizzle row)
+};
+
+// Row-major [outer, inner] tensor with leading dimension ld (elements).
+static int make_map_kind(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
+                         uint64_t ld, uint32_t box_inner, uint32_t box_outer, MapKind kind) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, (uint32_t)kind};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -932,19 +944,26 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
       return 0;
     }
   }
+  const uint64_t esize = kind == MAP_F32_SW128 ? 4 : 2;
   PFN_encodeTiled enc = get_encode_fn();
   CC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   CC_REQUIRE(((uintptr_t)ptr & 15) == 0, "cc_gemm: operand base %p is not 16-byte aligned", ptr);
-  CC_REQUIRE((ld * 2) % 16 == 0, "cc_gemm: operand ld=%llu is not a multiple of 8 elements",
+  CC_REQUIRE((ld * esize) % 16 == 0, "cc_gemm: operand ld=%llu is not a multiple of 16 bytes",
              (unsigned long long)ld);
   CC_REQUIRE(inner > 0 && outer > 0, "cc_gemm: empty operand");
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * esize};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out,
+                   kind == MAP_F32_SW128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kind == MAP_BF16_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   kind == MAP_BF16_SW128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CC_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
              (int)r, ptr, (unsigned long long)inner, (unsigned long long)outer,
@@ -955,6 +974,12 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t 
     cache.emplace(key, *out);
   }
   return 0;
+}
+
+// bf16 GEMM operand
+static int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
+  return make_map_kind(out, ptr, inner, outer, ld, box_inner, box_outer, MAP_BF16_SW128);
 }
 
 // smem matrix descriptor without the start address (cute::UMMA::SmemDescriptor):
@@ -1082,6 +1107,55 @@ static int launch_persistent(const TmaMaps& maps, const GemmParams& p, int mt, i
   const bool math = e.alpha != 1.f || e.bias != nullptr || e.act != 0 || e.dact != 0;
   if (math) return launch_persistent_m<BN, STAGES, true>(maps, p, mt, nt, num_sms, a_mn, b_mn, st);
   return launch_persistent_m<BN, STAGES, false>(maps, p, mt, nt, num_sms, a_mn, b_mn, st);
+}
+
+template <bool N_FAST, int CLUSTER>
+static int launch_rms_tma(const RmsMaps& maps, const GemmParams& p, int mt, int nt, int num_sms,
+                          cudaStream_t st) {
+  auto kern = wgrad_rmsprop_tma_kernel<N_FAST, CLUSTER>;
+  static bool attr_set = false;
+  static int max_ctas = 0;
+  constexpr size_t smem = RMS_SMEM_BYTES;
+  constexpr int threads = 64 + 32 * RMS_EPI_WARPS;
+  if (!attr_set) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    max_ctas = num_sms;
+    if (CLUSTER > 1) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3((unsigned)(num_sms / CLUSTER * CLUSTER));
+      q.blockDim = dim3(threads);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CLUSTER;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int nclusters = 0;
+      CC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, kern, &q));
+      CC_REQUIRE(nclusters >= 1, "cc_gemm: no %d-CTA cluster fits on this device", CLUSTER);
+      if (nclusters * CLUSTER < max_ctas) max_ctas = nclusters * CLUSTER;
+    }
+    attr_set = true;
+  }
+  const int units = ((mt + CLUSTER - 1) / CLUSTER) * nt;
+  int grid = units * CLUSTER < max_ctas ? units * CLUSTER : max_ctas / CLUSTER * CLUSTER;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p, mt, nt));
+  count_launch();
+  return 0;
 }
 
 static int g_num_sms = 0;
@@ -1280,6 +1354,37 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       // CTAs of a wave share one B tile and A (X^T) is the L2-resident operand
       int nfast = env_int("CC_GEMM_RMS_NFAST", -1);
       if (nfast < 0) nfast = ((long long)total * BK * d->N * 2 <= (48ll << 20)) ? 1 : 0;
+      // optimiser state moved by TMA (wgrad_rmsprop_kernel.cuh) whenever the parameter block is
+      // TMA-addressable: 16-byte aligned bases and row pitch
+      const bool tma_ok =
+          env_int("CC_GEMM_RMS_TMA", 1) != 0 && (d->rms_ld & 7) == 0 && d->beta32 == 0 &&
+          ((((uintptr_t)d->rms_p32) | ((uintptr_t)d->rms_ms) | ((uintptr_t)d->rms_mom) |
+            ((uintptr_t)d->rms_p16)) & 15) == 0 && d->out16 == nullptr;
+      if (tma_ok) {
+        RmsMaps rm;
+        memset(&rm, 0, sizeof(rm));
+        for (int s = 0; s < d->nseg; ++s) {
+          rm.a[s] = maps.a[s];
+          rm.b[s] = maps.b[s];
+        }
+        int rc = make_map_kind(&rm.p32, d->rms_p32, (uint64_t)d->N, (uint64_t)d->M,
+                               (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+        if (!rc) rc = make_map_kind(&rm.ms, d->rms_ms, (uint64_t)d->N, (uint64_t)d->M,
+                                    (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+        if (!rc) rc = make_map_kind(&rm.mom, d->rms_mom, (uint64_t)d->N, (uint64_t)d->M,
+                                    (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+        if (!rc && d->rms_p16 != nullptr)
+          rc = make_map_kind(&rm.p16, d->rms_p16, (uint64_t)d->N, (uint64_t)d->M,
+                             (uint64_t)d->rms_ld, 32, 32, MAP_BF16_SW64);
+        if (rc) return rc;
+        // bit 1: bf16 weight copy written by row stores from registers instead of a TMA store
+        if (env_int("CC_GEMM_RMS_P16_TMA", 0) == 0) p.epi.rms_cs |= 2;
+        if (p.cluster == 2)
+          return nfast ? launch_rms_tma<true, 2>(rm, p, mt, nt, g_num_sms, st)
+                       : launch_rms_tma<false, 2>(rm, p, mt, nt, g_num_sms, st);
+        return nfast ? launch_rms_tma<true, 1>(rm, p, mt, nt, g_num_sms, st)
+                     : launch_rms_tma<false, 1>(rm, p, mt, nt, g_num_sms, st);
+      }
       if (nfast != 0)
         return launch_persistent_cfg<256, 3, true, true, false, 8, true>(maps, p, mt, nt, g_num_sms, st);
       return launch_persistent_cfg<256, 3, true, true, false, 8>(maps, p, mt, nt, g_num_sms, st);

@@ -48,6 +48,12 @@ struct PeerPtrs {
   const float* g[CC_PEER_MAX];
   bf16* p16[CC_PEER_MAX];
 };
+// low-order terms of the kernels kept as hi + lo: only inside [begin, end) x 2
+struct PeerLo {
+  bf16* p16lo[CC_PEER_MAX];
+  bf16* mc;
+  long long begin[2], end[2];
+};
 
 __global__ void __launch_bounds__(256)
 peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
@@ -55,7 +61,7 @@ peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
                     const long long count, const int broadcast, const float lr, const float rho,
                     const float momentum, const float eps, const uint32_t* ready,
                     const uint32_t epoch_rel, const uint32_t* __restrict__ epoch_ctr,
-                    bf16* __restrict__ p16_mc) {
+                    bf16* __restrict__ p16_mc, const PeerLo lo) {
   // epochs: host value, or (CUDA-graph friendly) a device counter plus a constant
   const uint32_t epoch = epoch_rel + (epoch_ctr ? *epoch_ctr : 0u);
   // every rank's gradient for this bucket must be complete (and, because the flags are only
@@ -121,6 +127,37 @@ peer_rmsprop_kernel(const PeerPtrs pp, const int world, float* __restrict__ p32,
     } else {
       *reinterpret_cast<uint4*>(pp.p16[0] + off) = u;   // replicated update: local copy only
     }
+    if (lo.p16lo[0] != nullptr &&
+        ((off >= lo.begin[0] && off < lo.end[0]) || (off >= lo.begin[1] && off < lo.end[1]))) {
+      // hi + lo kernels: the low-order term travels the same way
+      uint4 v;
+      {
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&u);
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 h = __bfloat1622float2(hp[k]);
+          r[2 * k] = w[2 * k] - h.x;
+          r[2 * k + 1] = w[2 * k + 1] - h.y;
+        }
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(r[0], r[1]), l1 = __floats2bfloat162_rn(r[2], r[3]);
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(r[4], r[5]), l3 = __floats2bfloat162_rn(r[6], r[7]);
+        v.x = *reinterpret_cast<uint32_t*>(&l0);
+        v.y = *reinterpret_cast<uint32_t*>(&l1);
+        v.z = *reinterpret_cast<uint32_t*>(&l2);
+        v.w = *reinterpret_cast<uint32_t*>(&l3);
+      }
+      if (broadcast && lo.mc != nullptr) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(lo.mc + off),
+                     "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                     "f"(__uint_as_float(v.w))
+                     : "memory");
+      } else if (broadcast) {
+        for (int q = 0; q < world; ++q) *reinterpret_cast<uint4*>(lo.p16lo[q] + off) = v;
+      } else {
+        *reinterpret_cast<uint4*>(lo.p16lo[0] + off) = v;
+      }
+    }
   }
 }
 
@@ -165,6 +202,16 @@ extern "C" int cc_peer_rmsprop(const cc_peer_rmsprop_desc* d, cc_stream_t stream
                "cc_peer_rmsprop: missing peer pointer %d", q);
   }
   if (!d->broadcast) pp.p16[0] = (bf16*)d->p16[d->rank];
+  PeerLo lo;
+  for (int q = 0; q < CC_PEER_MAX; ++q) lo.p16lo[q] = q < d->world ? (bf16*)d->p16lo[q] : nullptr;
+  if (lo.p16lo[0] != nullptr && !d->broadcast) lo.p16lo[0] = (bf16*)d->p16lo[d->rank];
+  lo.mc = (bf16*)d->p16lo_multicast;
+  for (int k = 0; k < 2; ++k) {
+    lo.begin[k] = d->lo_begin[k];
+    lo.end[k] = d->lo_end[k];
+    CC_REQUIRE((lo.begin[k] & 7) == 0 && (lo.end[k] & 7) == 0,
+               "cc_peer_rmsprop: hi+lo range %d must be 8-element granular", k);
+  }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -183,7 +230,7 @@ extern "C" int cc_peer_rmsprop(const cc_peer_rmsprop_desc* d, cc_stream_t stream
   if (blocks > cap) blocks = cap;
   peer_rmsprop_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       pp, d->world, d->p32, d->ms, d->mom, d->start, d->count, d->broadcast, d->lr, d->rho,
-      d->momentum, d->eps, d->ready, d->epoch, d->epoch_ctr, (bf16*)d->p16_multicast);
+      d->momentum, d->eps, d->ready, d->epoch, d->epoch_ctr, (bf16*)d->p16_multicast, lo);
   CC_CHECK_LAUNCH();
   return 0;
 }

@@ -42,6 +42,8 @@ _SHARD_OPTIMIZER = os.environ.get("CELLCOMM_B200_SHARD_OPT", "1") != "0"
 # diagnostic: data-parallel step without gradient exchange / update (compute-only lower bound)
 _DP_SKIP_UPDATE = os.environ.get("CELLCOMM_B200_DP_SKIP_UPDATE", "0") == "1"
 _BUCKET_ELEMS = int(os.environ.get("CELLCOMM_B200_BUCKET_ELEMS", str(48 << 20)))
+# hi + lo bf16 compute copies of the BN-feeding kernels of level-3 networks (the generator)
+_HILO_WEIGHTS = os.environ.get("CELLCOMM_B200_HILO_WEIGHTS", "1") != "0"
 
 
 # =========================================================================== graph specs
@@ -360,6 +362,7 @@ class Net:
         self.max_rows = int(max_rows)
         self.device = device
         self.dist = dist or _NoDist()
+        self.hp, self.split = self._high_precision_tensors()
         self._alloc_params(generator)
         self._build_buckets()
         self.act = {}      # forward activations (bf16; fp32 for tensors in self.hp)
@@ -377,7 +380,6 @@ class Net:
         self._slots_stale = False
         self.fuse_optimizer = False   # kernels updated inside the wgrad epilogue (1 GPU)
         self.keep_grads = False       # fused mode: also write dW (parity tests)
-        self.hp, self.split = self._high_precision_tensors()
         self.split_lo = {}  # bf16 low-order terms of the split tensors
         self._needs_cache = {}
         self._ctx = None
@@ -445,6 +447,22 @@ class Net:
         else:
             self.g32 = torch.zeros_like(self.p32)
             self.p16 = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
+        # low-order bf16 term of the kernels kept as hi + lo (flat, same layout; only the
+        # ranges of the `hilo` layers are ever non-zero / read)
+        self.p16lo = None
+        if self.hilo:
+            if self.peer is not None:
+                self.p16lo, lo_ptrs, h4 = sym(self.n_flat, ops.COMPUTE_DTYPE, dev)
+                lo_mc = 0
+                if self.peer["p16_mc"]:
+                    try:
+                        lo_mc = int(h4.multicast_ptr or 0)
+                    except Exception:
+                        lo_mc = 0
+                self.peer.update(p16lo=lo_ptrs, p16lo_mc=lo_mc)
+                self.peer["handles"].append(h4)
+            else:
+                self.p16lo = torch.zeros(self.n_flat, dtype=ops.COMPUTE_DTYPE, device=dev)
         self.layers = []
         for m in meta:
             L = dict(m)
@@ -454,6 +472,8 @@ class Net:
                 bv = lambda buf: buf[m["b_off"]:m["b_off"] + N]
                 L.update(w32=wv(self.p32), w16=wv(self.p16), dw=wv(self.g32), b32=bv(self.p32),
                          db=bv(self.g32), ms_w=wv(self.ms), mom_w=wv(self.mom))
+                if len(self.layers) in self.hilo:
+                    L["w16lo"] = wv(self.p16lo)
                 fan = K + N
                 if K > 0 and N > 0:
                     limit = math.sqrt(6.0 / fan)      # glorot_uniform (Keras Dense default)
@@ -530,8 +550,25 @@ class Net:
             self.peer["handles"].append(h3)
 
     def sync_compute_copy(self):
-        """bf16 compute copy <- fp32 master (after init / set_weights)."""
+        """bf16 compute copy (and the low-order terms of the hi + lo kernels) <- fp32 master
+        (after init / set_weights)."""
         self.p16.copy_(self.p32)
+        self.refresh_lo()
+
+    def hilo_ranges(self):
+        """flat [start, end) ranges of the kernels kept as hi + lo"""
+        return [(self.layers[i]["w_off"], self.layers[i]["w_off"] + self.layers[i]["K"] * self.layers[i]["ld"])
+                for i in sorted(self.hilo)]
+
+    def refresh_lo(self, start=None, end=None):
+        """lo = bf16(w32 - bf16(w32)) over the hi + lo kernels (restricted to the flat range
+        [start, end) when given: the shard this rank just updated)."""
+        for a, b in self.hilo_ranges():
+            if start is not None:
+                a, b = max(a, start), min(b, end)
+            if b > a:
+                ops.split_bf16(self.p32[a:b].view(1, -1), self.p16[a:b].view(1, -1),
+                               self.p16lo[a:b].view(1, -1))
 
     def param_count(self):
         n = 0
@@ -607,11 +644,19 @@ class Net:
         # over the batch, so wgrad / dgrad / the bias gradient of the layer below are
         # cancellation-dominated and need dz as hi + lo as well.
         self.prebn = set()
+        # layers whose bf16 compute copy of the KERNEL is kept as hi + lo as well (level 3): the
+        # rounding of a BN-feeding kernel is amplified by 1/std of the batch like everything else
+        # on the way into the BN; with W = hi + lo the forward and the input gradient of these
+        # layers see the fp32 master weights to 16 mantissa bits (DESIGN.md "precision policy")
+        self.hilo = set()
         if self.precision >= 2:
             for n in g.nodes:
                 if n["kind"] == "dense" and n["out"] in hp:
                     if self.precision >= 3:
                         self.prebn.add(n["out"])
+                        if _HILO_WEIGHTS and g.widths[n["out"]] > 0 and \
+                                sum(g.widths[i] for i in n["ins"]) > 0:
+                            self.hilo.add(n["layer"])
                     split.update(i for i in n["ins"] if i in producer and g.widths[i] > 0)
         if self.precision >= 1:
             # narrow tensors (latents, the 50..256-wide trunks, the encoder tail): fp32 + hi/lo
@@ -749,15 +794,23 @@ class Net:
                 elif wants_out32:
                     dest32 = out32
                 if width > 0:
-                    xs, offs, ro = [], [], 0
+                    segs, second, ro = [], [], 0          # (operand, kernel row offset, kernel)
+                    wlo = L.get("w16lo")
                     for i in node["ins"]:
                         if g.widths[i] > 0:
-                            for term in self._gemm_operands(A, i, rows):
-                                xs.append(term)
-                                offs.append(ro)
+                            terms = self._gemm_operands(A, i, rows)
+                            segs += [(t, ro, L["w16"]) for t in terms]
+                            if wlo is not None:
+                                # kernel kept as hi + lo: x_hi @ W_lo, and the second-order
+                                # x_lo @ W_lo while the segment list has room for it
+                                segs.append((terms[0], ro, wlo))
+                                second += [(t, ro, wlo) for t in terms[1:]]
                         ro += g.widths[i]
+                    if len(segs) + len(second) <= 4:     # CC_GEMM_MAX_SEG
+                        segs += second
+                    xs, offs, ws = ([sg[j] for sg in segs] for j in range(3))
                     if xs:
-                        ops.dense_fwd(xs, L["w16"], offs, L["b32"], act, out16=dest16, out32=dest32)
+                        ops.dense_fwd(xs, ws, offs, L["b32"], act, out16=dest16, out32=dest32)
                     else:
                         ops.bias_act(L["b32"], act, rows, out16=dest16, out32=dest32)
                     if copy_out is not None:
@@ -893,8 +946,12 @@ class Net:
                         if needs[i]:
                             wseg = L["w16"][ro:ro + k]
                             dst = self._buf(self.grad, i)[:rows]
-                            ops.dense_dgrad(dzs, [wseg] * len(dzs), dst,
-                                            beta=1 if state[i] else 0)
+                            d_terms, w_terms = list(dzs), [wseg] * len(dzs)
+                            if "w16lo" in L:         # dz_hi @ W_lo^T (+ dz_lo @ W_lo^T)
+                                for d_ in dzs[:4 - len(dzs)]:
+                                    d_terms.append(d_)
+                                    w_terms.append(L["w16lo"][ro:ro + k])
+                            ops.dense_dgrad(d_terms, w_terms, dst, beta=1 if state[i] else 0)
                             state[i] = True
                         if train:
                             xs = c["operands"][i]
@@ -925,6 +982,9 @@ class Net:
                     if out in self.prebn:
                         ops.bias_grad(dy, A[out], 0, L["db"])     # dy already holds dz (fp32)
                     # (other layers: done together with dz above)
+                    if self.fuse_optimizer and "w16lo" in L:
+                        # the wgrad epilogues above just updated this kernel: new low-order term
+                        ops.split_bf16(L["w32"], L["w16"], L["w16lo"])
             elif kind == "softmax":
                 i = node["ins"][0]
                 if width > 0 and needs[i]:
@@ -1041,7 +1101,12 @@ class Net:
             self.dist.reduce_scatter(shard, self.g32[bk["start"]:bk["end"]])
             ops.rmsprop_step(self.p32[sl], self.p16[sl], shard, self.ms[sl], self.mom[sl], LR, RHO,
                              MOMENTUM, EPSILON)
+            has_lo = any(a < bk["end"] and b > bk["start"] for a, b in self.hilo_ranges())
+            if has_lo:
+                self.refresh_lo(sl.start, sl.stop)
             self.dist.all_gather(self.p16[bk["start"]:bk["end"]], self.p16[sl])
+            if has_lo:
+                self.dist.all_gather(self.p16lo[bk["start"]:bk["end"]], self.p16lo[sl])
 
         if self.opt_stream is None:
             run()
@@ -1073,9 +1138,12 @@ class Net:
             grads = [pr["stage"][r] + 4 * q * self.n_flat for q in range(W)]
         else:           # replicated tail: pull every rank's own (small) gradient
             grads = [pr["stage"][q] + 4 * q * self.n_flat for q in range(W)]
+        lo = None
+        if self.hilo and broadcast:
+            lo = (pr["p16lo"], pr["p16lo_mc"], self.hilo_ranges())
         ops.peer_rmsprop(W, r, grads, pr["p16"], self.p32, self.ms, self.mom, start, count,
                          broadcast, LR, RHO, MOMENTUM, EPSILON, self._flag_ptr(r, 0, bucket, 0),
-                         1, p16_multicast=pr["p16_mc"], epoch_ctr=pr["ctr"])
+                         1, p16_multicast=pr["p16_mc"], epoch_ctr=pr["ctr"], lo=lo)
         ops.peer_signal([self._flag_ptr(t, 1, bucket, r) for t in range(W)], 1, epoch_ctr=pr["ctr"])
 
     def _reduce_and_update(self):
@@ -1112,6 +1180,7 @@ class Net:
             self.dist.all_reduce(self.g32)
             ops.rmsprop_step(self.p32, self.p16, self.g32, self.ms, self.mom, LR, RHO, MOMENTUM,
                              EPSILON)
+            self.refresh_lo()
             return
         n = K // W
         sl = slice(self.dist.rank * n, (self.dist.rank + 1) * n)
@@ -1120,7 +1189,11 @@ class Net:
         self.dist.reduce_scatter(self._gshard, self.g32[:K])
         ops.rmsprop_step(self.p32[sl], self.p16[sl], self._gshard, self.ms[sl], self.mom[sl], LR,
                          RHO, MOMENTUM, EPSILON)
+        if self.hilo:
+            self.refresh_lo(sl.start, sl.stop)
         self.dist.all_gather(self.p16[:K], self.p16[sl])
+        if self.hilo:
+            self.dist.all_gather(self.p16lo[:K], self.p16lo[sl])
         # biases and BN gamma/beta are read in fp32 by the forward kernels: replicated update
         tail = slice(K, self.n_flat)
         self.dist.all_reduce(self.g32[tail])
@@ -1502,6 +1575,7 @@ class BiGanEngine:
         for k, n in self.nets.items():
             snap[k] = {"p32": n.p32.clone(), "p16": n.p16.clone(), "ms": n.ms.clone(),
                        "mom": n.mom.clone(),
+                       "p16lo": None if n.p16lo is None else n.p16lo.clone(),
                        "bn": [(L["moving_mean"].clone(), L["moving_var"].clone())
                               for L in n.layers if L["kind"] == "bn"]}
         return snap
@@ -1515,6 +1589,8 @@ class BiGanEngine:
             n.p16.copy_(s["p16"])
             n.ms.copy_(s["ms"])
             n.mom.copy_(s["mom"])
+            if n.p16lo is not None:
+                n.p16lo.copy_(s["p16lo"])
             for L, (mm, mv) in zip([L for L in n.layers if L["kind"] == "bn"], s["bn"]):
                 L["moving_mean"].copy_(mm)
                 L["moving_var"].copy_(mv)
@@ -1690,6 +1766,8 @@ class BiGanEngine:
             kind, out = node["kind"], node["out"]
             if kind == "dense":
                 L = net.layers[node["layer"]]
+                if "w16lo" in L:
+                    return None                          # hi + lo kernels: not expressible
                 segs, ro = [], 0
                 for i in node["ins"]:
                     for term in gemm_operands(i):

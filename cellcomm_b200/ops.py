@@ -133,8 +133,9 @@ def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
 
     xs: list of [M, K_s] bf16 (Concatenate segments, consumed without materialising);
     w16: [K_total, N] bf16 Keras-layout kernel.  Dense forward, src/bigan_classify.py:10-75."""
-    M, N = xs[0].shape[0], w16.shape[1]
-    bs = [w16[ro:ro + x.shape[1]] for x, ro in zip(xs, row_offsets)]
+    ws = list(w16) if isinstance(w16, (list, tuple)) else [w16] * len(xs)   # per-segment kernels
+    M, N = xs[0].shape[0], ws[0].shape[1]
+    bs = [w[ro:ro + x.shape[1]] for x, w, ro in zip(xs, ws, row_offsets)]
     if out16 is not None and out16.dtype == torch.float32:   # fp32 activation (feeds a BN)
         if out32 is not None:
             raise ValueError("dense_fwd: two fp32 outputs")
@@ -401,7 +402,7 @@ def fill_f32(t, value):
 
 # --------------------------------------------------------------------------- peer-memory optimiser
 def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, broadcast, lr, rho,
-                 momentum, eps, ready_ptr, epoch, p16_multicast=0, epoch_ctr=None):
+                 momentum, eps, ready_ptr, epoch, p16_multicast=0, epoch_ctr=None, lo=None):
     """Fused reduce-scatter -> Keras RMSprop -> bf16 all-gather over NVLink peer memory for the
     flat element range [start, start+count).  grad_ptrs / p16_ptrs: device pointers (ints) of
     every rank's flat gradient / bf16 weight buffer; p32, ms, mom: this rank's flat buffers."""
@@ -417,6 +418,17 @@ def peer_rmsprop(world, rank, grad_ptrs, p16_ptrs, p32, ms, mom, start, count, b
     d.ready, d.epoch = int(ready_ptr), int(epoch) & 0xFFFFFFFF
     d.p16_multicast = int(p16_multicast) or None
     d.epoch_ctr = _p(epoch_ctr)
+    if lo is not None:
+        # lo = (p16lo_ptrs, p16lo_multicast, [(begin, end), ...]): low-order terms of the
+        # kernels kept as hi + lo (at most two flat ranges)
+        lo_ptrs, lo_mc, ranges = lo
+        if len(ranges) > 2:
+            raise ValueError("peer_rmsprop: at most two hi+lo ranges")
+        for q in range(world):
+            d.p16lo[q] = int(lo_ptrs[q])
+        d.p16lo_multicast = int(lo_mc) or None
+        for k, (a, b) in enumerate(ranges):
+            d.lo_begin[k], d.lo_end[k] = int(a), int(b)
     check(_lib.load().cc_peer_rmsprop(C.byref(d), _stream()))
 
 

@@ -88,8 +88,9 @@ int cc_coo_build_csr(const cc_coo* coo, cc_csr** out);
  * and the DataFrame -> float32 tensor feed of train_on_batch/predict.
  * row_idx_dev != NULL: output row i is CSR row row_idx_dev[i] (sampled batch);
  * row_idx_dev == NULL: output row i is CSR row row_start + i (encode-all pass).
- * out16/out32 may each be NULL.  Rows are fully written (zeros where the CSR
- * has no entry) for columns [0, ld).
+ * out16/out32 may each be NULL.  Columns [0, n_cols) of every output row are written (zeros
+ * where the CSR has no entry); the padding columns [n_cols, ld) are not touched, so an output
+ * may be a column slice of a wider buffer.
  */
 int cc_gather_rows(const int64_t* rowptr_dev, const int32_t* colidx_dev, const float* values_dev,
                    const int64_t* row_idx_dev, int64_t row_start, int64_t n_rows, int64_t n_cols,
@@ -369,6 +370,13 @@ typedef struct cc_peer_rmsprop_desc {
    * the updated weights to every rank, instead of world P2P stores (7/8 less NVLink egress
    * for the all-gather at 8 GPUs).  NULL: P2P stores. */
   void* p16_multicast;
+  /* optional low-order bf16 term (kernels kept as hi + lo, see cc_split_bf16): for elements of
+   * the flat ranges [lo_begin[k], lo_end[k]), k < 2, the kernel also delivers
+   * bf16(w - float(bf16(w))) to every rank's p16lo buffer (p16lo_multicast when non-NULL).
+   * p16lo[0] == NULL: off. */
+  void* p16lo[CC_PEER_MAX];
+  void* p16lo_multicast;
+  int64_t lo_begin[2], lo_end[2];
 } cc_peer_rmsprop_desc;
 int cc_peer_rmsprop(const cc_peer_rmsprop_desc* desc, cc_stream_t stream);
 int cc_peer_signal(uint32_t* const* targets, int32_t n, uint32_t value,

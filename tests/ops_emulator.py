@@ -48,9 +48,10 @@ def _store(dst, v, beta=0):
 
 
 def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
+    ws = list(w16) if isinstance(w16, (list, tuple)) else [w16] * len(xs)
     acc = 0
-    for x, ro in zip(xs, row_offsets):
-        acc = acc + x.double() @ w16[ro:ro + x.shape[1]].double()
+    for x, w, ro in zip(xs, ws, row_offsets):
+        acc = acc + x.double() @ w[ro:ro + x.shape[1]].double()
     v = _act(acc + bias.double(), act).float()
     _store(out16, v)
     if out32 is not None:

@@ -136,6 +136,16 @@ def test_run_with_interceptors_matches_oracle(tmp_path, monkeypatch, graph):
     enc_files = intercepts.EncodingFiles(log_dir)
     checked = []
 
+    # per-step losses, recorded around the public method the trainer calls
+    per_step, inner = [], net.trainings_step
+
+    def recording_step(batch):
+        out = inner(batch)
+        per_step.append(out)
+        return out
+
+    net.trainings_step = recording_step
+
     def against_oracle(it, losses):
         got = [float(v) for v in losses]
         ref = np.zeros(3)
@@ -143,9 +153,16 @@ def test_run_with_interceptors_matches_oracle(tmp_path, monkeypatch, graph):
             step = it * BPI + b
             pos, enc, noise = feed[step]
             masks = _engine_masks(eng, step, B)
-            ref += np.array(orc.trainings_step(torch.from_numpy(dense[pos]), enc, noise, masks))
-        for a, r in zip(got, ref):
-            assert abs(a - r) <= 3e-2 * abs(r) + 3e-3, f"iteration {it}: losses {got} vs {ref}"
+            one = np.array(orc.trainings_step(torch.from_numpy(dense[pos]), enc, noise, masks))
+            mine = np.array([float(v) for v in per_step[step]])
+            # first step of an iteration: identical weights (rel 1e-2); the second one runs
+            # free after six RMSprop updates on each side (see tests/test_parity_gpu.py)
+            rel, ab = (1e-2, 2e-3) if b == 0 else (8e-2, 5e-3)
+            assert np.all(np.abs(mine - one) <= rel * np.abs(one) + ab), \
+                f"iteration {it} step {b}: losses {mine} vs oracle {one}"
+            ref += one
+        assert np.allclose(got, [sum(float(s[j]) for s in per_step[it * BPI:(it + 1) * BPI])
+                                 for j in range(3)], rtol=1e-6), "run() must sum the step losses"
         # encode-all-cells from IDENTICAL weights: oracle <- engine, then both encode all cells
         _sync_oracle(orc, eng)
         checked.append((it, orc.encoding_prediction(torch.from_numpy(dense)).numpy()))

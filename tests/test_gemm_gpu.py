@@ -235,6 +235,62 @@ def test_wgrad_with_fused_rmsprop_epilogue(K, N, B):
     assert torch.equal(p32b, p32) and torch.equal(msb, ms)
 
 
+@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("nfast", ["0", "1"])
+@pytest.mark.parametrize("K,N,B", [(1000, 1300, 256), (385, 2049, 96), (64, 300, 40)])
+def test_fused_rmsprop_epilogue_paths(K, N, B, nfast, tma, monkeypatch):
+    """The two fused-optimiser epilogues (tma = "1": optimiser state moved by TMA through
+    swizzled shared memory, wgrad_rmsprop_kernel.cuh; "0": register path of the generic
+    persistent kernel), both tile rasters, several row / column tiles with ragged edges, 2-CTA
+    clusters (K >= 256) and a single row tile (K = 64), with and without the bf16 copy, with
+    and without the gradient output.  Padding columns must stay untouched."""
+    ops = _ops()
+    monkeypatch.setenv("CC_GEMM_RMS_TMA", tma)
+    monkeypatch.setenv("CC_GEMM_RMS_NFAST", nfast)
+    x, dz = _rand(B, K, 90, 0.5), _rand(B, N, 91, 0.01)
+    ld = ops.pad_ld(N)
+    w0 = torch.randn(K, N) * 0.05
+    ms0 = torch.rand(K, N) * 1e-4
+    mom0 = torch.randn(K, N) * 1e-3
+    lr, rho, mo, eps = 0.0075, 0.85, 0.1, 1e-7
+
+    def mk(t, dt=torch.float32):
+        full = torch.full((K, ld), 7.0, dtype=dt, device="cuda")
+        full[:, :N].copy_(t)
+        return full
+
+    g = x.float().t() @ dz.float()
+    ms_ref = rho * ms0 + (1 - rho) * g * g
+    mom_ref = mo * mom0 + lr * g / torch.sqrt(ms_ref + eps)
+    for with16, with_grad in ((True, False), (False, True), (True, True)):
+        p32f, msf, momf = mk(w0), mk(ms0), mk(mom0)
+        p16f = torch.full((K, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        dwf = torch.full((K, ld), 7.0, device="cuda")
+        ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), dwf[:, :N] if with_grad else None,
+                        rms=(p32f[:, :N], p16f[:, :N] if with16 else None, msf[:, :N], momf[:, :N],
+                             lr, rho, mo, eps))
+        torch.cuda.synchronize()
+        # bf16 operands, fp32 accumulation: the gradient itself is checked loosely, the update
+        # arithmetic against the kernel's own gradient where available
+        assert torch.allclose(msf[:, :N].cpu(), ms_ref, rtol=2e-2, atol=1e-9)
+        assert torch.allclose(momf[:, :N].cpu(), mom_ref, rtol=2e-2, atol=2e-5)
+        assert torch.allclose(p32f[:, :N].cpu(), w0 - mom_ref, rtol=0, atol=3e-5)
+        if with_grad:
+            gk = dwf[:, :N].cpu()
+            _check(dwf[:, :N], g, B, False, scale=0.005)
+            ms_k = rho * ms0 + (1 - rho) * gk * gk
+            mom_k = mo * mom0 + lr * gk / torch.sqrt(ms_k + eps)
+            assert torch.allclose(msf[:, :N].cpu(), ms_k, rtol=1e-5, atol=1e-12)
+            assert torch.allclose(momf[:, :N].cpu(), mom_k, rtol=1e-4, atol=1e-8)
+            assert torch.allclose(p32f[:, :N].cpu(), w0 - mom_k, rtol=1e-5, atol=1e-7)
+            assert float((dwf[:, N:] - 7.0).abs().sum()) == 0.0
+        if with16:
+            assert torch.equal(p16f[:, :N], p32f[:, :N].to(torch.bfloat16))
+        # padding columns [N, ld) are never written (TMA clips stores at the tensor bounds)
+        for t in (p32f, msf, momf, p16f):
+            assert float((t[:, N:].float() - 7.0).abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("bn_eff", [128, 160, 192, 224, 256])
 @pytest.mark.parametrize("orient", ["fwd", "dgrad", "wgrad"])
 def test_effective_tile_width(bn_eff, orient, monkeypatch):

@@ -50,6 +50,18 @@ def pair():
     torch.cuda.empty_cache()
 
 
+def _log(rec):
+    """one JSON line per comparison (pytest -s shows them; CELLCOMM_PARITY_LOG=path keeps them)"""
+    import json
+    import os
+    line = json.dumps(rec)
+    print(line)
+    path = os.environ.get("CELLCOMM_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(line + "\n")
+
+
 def _dots(a, b):
     a, b = a.double().reshape(-1), b.double().reshape(-1)
     return float(a @ b), float(a @ a), float(b @ b)
@@ -98,15 +110,21 @@ def _check_update(p, k, x16, xo, zo, ro, masks, dmasks, B, *, resync=True):
             continue
         gd.append(_dots(dw, rg.cuda()))
         ud.append(_dots(w - w0, rw.cuda() - w0))
+    failures = []
     for what, dots, flat_min, tensor_min in (("gradient", gd, P.GRAD_FLAT, P.GRAD_TENSOR),
                                              ("update", ud, P.UPD_FLAT, P.UPD_TENSOR)):
         flat = _cos3(tuple(sum(d[i] for d in dots) for i in range(3)))
-        assert flat >= flat_min, f"sub-step {k} {name} (B={B}): flat {what} cosine {flat}"
         total = sum(d[2] for d in dots) ** 0.5
-        for i, d in enumerate(dots):
-            if d[2] ** 0.5 >= 2e-2 * total:
-                assert _cos3(d) >= tensor_min, \
-                    f"sub-step {k} {name} (B={B}) tensor {i}: {what} cosine {_cos3(d)}"
+        per = {i: _cos3(d) for i, d in enumerate(dots) if d[2] ** 0.5 >= 2e-2 * total}
+        worst = min(per.values()) if per else 1.0
+        _log({"substep": k, "net": name, "batch": B, "fused": bool(net.fuse_optimizer),
+              "what": what, "flat_cosine": flat, "worst_tensor_cosine": worst,
+              "loss": got_loss, "oracle_loss": ref_loss})
+        if flat < flat_min:
+            failures.append(f"sub-step {k} {name} (B={B}): flat {what} cosine {flat}")
+        for i, c in per.items():
+            if c < tensor_min:
+                failures.append(f"sub-step {k} {name} (B={B}) tensor {i}: {what} cosine {c}")
     # BN moving statistics of the trained network (momentum 0.99 update with batch statistics)
     for L, ol in zip(net.layers, p.orc.nets()[name]):
         if L["kind"] == "bn":
@@ -117,6 +135,7 @@ def _check_update(p, k, x16, xo, zo, ro, masks, dmasks, B, *, resync=True):
                     f"sub-step {k} {name}: {key} off by {err}"
     if resync:
         p.sync(name)
+    assert not failures, "; ".join(failures)
 
 
 def _stage(p, B, seed):
