@@ -1109,13 +1109,16 @@ static int launch_persistent(const TmaMaps& maps, const GemmParams& p, int mt, i
   return launch_persistent_m<BN, STAGES, false>(maps, p, mt, nt, num_sms, a_mn, b_mn, st);
 }
 
-template <bool N_FAST, int CLUSTER>
+template <bool N_FAST, int CLUSTER, bool PAIR = false>
 static int launch_rms_tma(const RmsMaps& maps, const GemmParams& p, int mt, int nt, int num_sms,
                           cudaStream_t st) {
-  auto kern = wgrad_rmsprop_tma_kernel<N_FAST, CLUSTER>;
+  static_assert(!PAIR || CLUSTER == 2, "the CTA pair is a cluster of two");
+  void (*kern)(const RmsMaps, const GemmParams, const int, const int);
+  if (PAIR) kern = wgrad_rmsprop_pair_kernel<N_FAST>;
+  else kern = wgrad_rmsprop_tma_kernel<N_FAST, CLUSTER>;
   static bool attr_set = false;
   static int max_ctas = 0;
-  constexpr size_t smem = RMS_SMEM_BYTES;
+  constexpr size_t smem = PAIR ? RMSP_SMEM_BYTES : RMS_SMEM_BYTES;
   constexpr int threads = 64 + 32 * RMS_EPI_WARPS;
   if (!attr_set) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1379,6 +1382,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
         if (rc) return rc;
         // bit 1: bf16 weight copy written by row stores from registers instead of a TMA store
         if (env_int("CC_GEMM_RMS_P16_TMA", 0) == 0) p.epi.rms_cs |= 2;
+        // bit 2: the two epilogue warps of a lane quarter interleave their 32-column blocks
+        if (env_int("CC_GEMM_RMS_INTERLEAVE", 1) != 0) p.epi.rms_cs |= 4;
+        // CTA pair (cta_group::2, 256-row tiles) whenever there are at least two row tiles
+        if (p.cluster == 2 && env_int("CC_GEMM_RMS_PAIR", 1) != 0)
+          return nfast ? launch_rms_tma<true, 2, true>(rm, p, mt, nt, g_num_sms, st)
+                       : launch_rms_tma<false, 2, true>(rm, p, mt, nt, g_num_sms, st);
         if (p.cluster == 2)
           return nfast ? launch_rms_tma<true, 2>(rm, p, mt, nt, g_num_sms, st)
                        : launch_rms_tma<false, 2>(rm, p, mt, nt, g_num_sms, st);
