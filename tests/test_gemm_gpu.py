@@ -235,17 +235,24 @@ def test_wgrad_with_fused_rmsprop_epilogue(K, N, B):
     assert torch.equal(p32b, p32) and torch.equal(msb, ms)
 
 
-@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("mode", ["pair", "tma", "tma16", "reg"])
 @pytest.mark.parametrize("nfast", ["0", "1"])
-@pytest.mark.parametrize("K,N,B", [(1000, 1300, 256), (385, 2049, 96), (64, 300, 40)])
-def test_fused_rmsprop_epilogue_paths(K, N, B, nfast, tma, monkeypatch):
-    """The two fused-optimiser epilogues (tma = "1": optimiser state moved by TMA through
-    swizzled shared memory, wgrad_rmsprop_kernel.cuh; "0": register path of the generic
-    persistent kernel), both tile rasters, several row / column tiles with ragged edges, 2-CTA
-    clusters (K >= 256) and a single row tile (K = 64), with and without the bf16 copy, with
-    and without the gradient output.  Padding columns must stay untouched."""
+@pytest.mark.parametrize("K,N,B", [(1000, 1300, 256), (385, 2049, 96), (64, 300, 40),
+                                   (700, 520, 2048)])
+def test_fused_rmsprop_epilogue_paths(K, N, B, nfast, mode, monkeypatch):
+    """The fused-optimiser epilogues -- "pair": CTA pair (tcgen05 cta_group::2, 256-row tiles)
+    with the optimiser state moved by TMA through swizzled shared memory; "tma": the same
+    epilogue on one-CTA tiles; "tma16": also the bf16 copy by TMA store; "reg": the register
+    path of the generic persistent kernel -- on both tile rasters, several row / column tiles
+    with ragged edges, a single row tile (K = 64: no cluster), a long batch reduction (32
+    k-blocks: the operand ring wraps many times), with and without the bf16 copy, with and
+    without the gradient output.  Padding must stay untouched, except that a TMA store clips at
+    16-byte granularity: up to 3 fp32 / 7 bf16 padding elements next to column N are rewritten
+    with the update of zeros, i.e. zeros (the engine's padding is zero and stays zero)."""
     ops = _ops()
-    monkeypatch.setenv("CC_GEMM_RMS_TMA", tma)
+    monkeypatch.setenv("CC_GEMM_RMS_TMA", "0" if mode == "reg" else "1")
+    monkeypatch.setenv("CC_GEMM_RMS_PAIR", "1" if mode == "pair" else "0")
+    monkeypatch.setenv("CC_GEMM_RMS_P16_TMA", "1" if mode == "tma16" else "0")
     monkeypatch.setenv("CC_GEMM_RMS_NFAST", nfast)
     x, dz = _rand(B, K, 90, 0.5), _rand(B, N, 91, 0.01)
     ld = ops.pad_ld(N)
@@ -286,9 +293,14 @@ def test_fused_rmsprop_epilogue_paths(K, N, B, nfast, tma, monkeypatch):
             assert float((dwf[:, N:] - 7.0).abs().sum()) == 0.0
         if with16:
             assert torch.equal(p16f[:, :N], p32f[:, :N].to(torch.bfloat16))
-        # padding columns [N, ld) are never written (TMA clips stores at the tensor bounds)
-        for t in (p32f, msf, momf, p16f):
-            assert float((t[:, N:].float() - 7.0).abs().sum()) == 0.0
+        # padding columns: untouched beyond the 16-byte granule that holds column N - 1
+        for t, tma_store in ((p32f, mode != "reg"), (msf, mode != "reg"), (momf, mode != "reg"),
+                             (p16f, mode == "tma16" and with16)):
+            per16 = 16 // t.element_size()
+            edge = (N + per16 - 1) // per16 * per16 if tma_store else N
+            assert float((t[:, edge:].float() - 7.0).abs().sum()) == 0.0
+            rim = t[:, N:edge].float()
+            assert bool(((rim == 7.0) | (rim == 0.0)).all())
 
 
 @pytest.mark.parametrize("bn_eff", [128, 160, 192, 224, 256])
