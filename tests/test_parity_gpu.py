@@ -7,12 +7,15 @@ operands with fp32 accumulation vs the oracle's fp32):
     losses            |got - ref| <= 1e-2 * |ref| + 1e-3          (every sub-step and g/e/d)
     encodings         per-cell cosine >= 0.999 and max abs err <= 2e-2
     gradients         from IDENTICAL weights (state synchronised from the oracle before every
-                      sub-step): whole-network flat gradient cosine >= 0.98; every parameter
-                      tensor that carries >= 2 % of the network's gradient norm: cosine >= 0.95
-                      (default precision level CELLCOMM_B200_SPLIT=1; level 3 reaches 0.99 /
-                      0.985, see tests/test_precision_budget.py and DESIGN.md)
+                      sub-step): whole-network flat gradient cosine >= 0.995; every parameter
+                      tensor that carries >= 2 % of the network's gradient norm: cosine >= 0.99
+                      (measured at the BASELINE shape: >= 0.998 / >= 0.997,
+                      profiles/r02_parity_baseline_shape.jsonl)
     RMSprop updates   (w_after - w_before) from identical weights and slots: flat cosine
-                      >= 0.99, tensors with >= 2 % of the update norm >= 0.95
+                      >= 0.99, tensors with >= 2 % of the update norm >= 0.95.  (With zero
+                      slots the first RMSprop step is lr/sqrt(1-rho) * sign(g): the update
+                      cosine counts sign flips of near-zero gradient entries, which is why its
+                      bar is lower than the gradient's.)
 
 Why gradients are compared per sub-step from synchronised weights: RMSprop's first step moves
 every weight by ~lr/sqrt(1-rho) = 0.019 whatever the gradient's size, which is larger than the
@@ -31,7 +34,7 @@ pytestmark = pytest.mark.gpu
 
 UPDATES = {1: "G", 2: "G", 3: "E", 4: "E", 6: "D", 8: "D"}
 # stated tolerances (cosines) -- also used by tests/test_parity_baseline_shape_gpu.py
-GRAD_FLAT, GRAD_TENSOR = 0.98, 0.95
+GRAD_FLAT, GRAD_TENSOR = 0.995, 0.99
 UPD_FLAT, UPD_TENSOR = 0.99, 0.95
 
 
