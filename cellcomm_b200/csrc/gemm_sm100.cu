@@ -1359,8 +1359,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       if (nfast < 0) nfast = ((long long)total * BK * d->N * 2 <= (48ll << 20)) ? 1 : 0;
       // optimiser state moved by TMA (wgrad_rmsprop_kernel.cuh) whenever the parameter block is
       // TMA-addressable: 16-byte aligned bases and row pitch
+      // (measured, profiles/r02_fused_rmsprop_tma_sweep.jsonl: ahead of the register epilogue
+      // while the batch reduction is short -- the reference's batch 128 -- and behind it when
+      // the operand ring is long, so the default follows the number of k-blocks)
+      int use_tma = env_int("CC_GEMM_RMS_TMA", -1);
+      if (use_tma < 0) use_tma = total <= 4 ? 1 : 0;
       const bool tma_ok =
-          env_int("CC_GEMM_RMS_TMA", 1) != 0 && (d->rms_ld & 7) == 0 && d->beta32 == 0 &&
+          use_tma != 0 && (d->rms_ld & 7) == 0 && d->beta32 == 0 &&
           ((((uintptr_t)d->rms_p32) | ((uintptr_t)d->rms_ms) | ((uintptr_t)d->rms_mom) |
             ((uintptr_t)d->rms_p16)) & 15) == 0 && d->out16 == nullptr;
       if (tma_ok) {
@@ -1385,7 +1390,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
         // bit 2: the two epilogue warps of a lane quarter interleave their 32-column blocks
         if (env_int("CC_GEMM_RMS_INTERLEAVE", 1) != 0) p.epi.rms_cs |= 4;
         // CTA pair (cta_group::2, 256-row tiles) whenever there are at least two row tiles
-        if (p.cluster == 2 && env_int("CC_GEMM_RMS_PAIR", 1) != 0)
+        if (p.cluster == 2 && env_int("CC_GEMM_RMS_PAIR", 0) != 0)
           return nfast ? launch_rms_tma<true, 2, true>(rm, p, mt, nt, g_num_sms, st)
                        : launch_rms_tma<false, 2, true>(rm, p, mt, nt, g_num_sms, st);
         if (p.cluster == 2)
