@@ -80,6 +80,7 @@ struct GemmParams {
   int b_boxes;            // MN-major B: 64-column TMA boxes per stage
   int b_half_rows;        // K-major B in a 2-CTA cluster: rows of the tile each CTA loads
   int cluster;            // 1 or 2 CTAs per cluster (persistent kernel)
+  int pair;               // cluster of 2 running one cta_group::2 MMA per k-step (256-row tiles)
   unsigned int stage_tx;  // bytes TMA delivers per stage
 };
 
@@ -666,17 +667,64 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+// ---- CTA pair (tcgen05 cta_group::2): one 256-row tile per SM pair ---------------------------
+// the cluster-space address of `local` (a shared::cta address) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+// TMA load whose completion bytes are counted on a barrier of the pair's LEADER CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map,
+                                                 uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 // N_FAST: consecutive tiles walk along N (the contiguous direction of the output / parameter
 // matrix), so the CTAs of one wave cover whole output rows: used by the fused-optimiser wgrad,
 // whose epilogue streams 26 B per element and wants DRAM-page-local bursts.
+//
+// PAIR (CLUSTER = 2 only): the SM pair runs ONE tcgen05 cta_group::2 MMA on a 256-row tile.  Each
+// CTA stages its own 128 rows of A and only its HALF of the B tile (the tensor cores fetch the
+// other half from the peer's shared memory), so a k-block costs 16 + 16 KB of shared memory per
+// CTA instead of 16 + 32 KB: the operand ring is 6 stages deep instead of 4 at the same L2 -> SM
+// traffic as the multicast scheme.  The leader CTA (cluster rank 0) issues every MMA; both
+// CTAs' TMA loads count on the leader's "full" barrier; tcgen05.commit is multicast to both
+// CTAs' "empty" / "accumulator full" barriers; each CTA drains its own 128 accumulator rows
+// from its own TMEM and reports "accumulator free" to the leader.
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false,
-          int CLUSTER = 1>
+          int CLUSTER = 1, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
                                const __grid_constant__ GemmParams p,
                                const int tiles_m, const int tiles_n) {
+  static_assert(!PAIR || CLUSTER == 2, "a CTA pair is a cluster of two");
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
@@ -710,22 +758,32 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CLUSTER);  // one commit from every CTA of the cluster
+      // pair: one arrival per CTA on the leader's barrier (plus the bytes of both)
+      mbar_init(full_bar(s), PAIR ? 2 : 1);
+      // one commit from every CTA of the cluster; pair: the leader's commit, multicast
+      mbar_init(empty_bar(s), PAIR ? 1 : CLUSTER);
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);  // one arrival per epilogue warp
+      // one arrival per epilogue warp (pair: of both CTAs, on the leader's barrier)
+      mbar_init(tempty_bar(a), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // one warp of EACH CTA: the pair gets the same columns in both TMEMs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -733,7 +791,48 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == 0 && PAIR) {
+    // ===================== TMA producer, CTA pair: own A rows + own half of B ================
+    uint32_t it = 0;
+    const int half = p.bn_eff / 2;
+    for (int u = unit0; u < num_units; u += unit_step) {
+      const int m0 = unit_m0(u), n0 = unit_n0(u) + rank * half;
+      int seg = 0, kb_in_seg = 0;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u, 11);
+        if (elect_one()) {
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_BYTES;
+          const uint32_t lbar = mapa_cluster(full_bar(s), 0);  // the leader's barrier
+          const int k0 = kb_in_seg * BK;
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * p.stage_tx);
+          else mbar_arrive_cluster(lbar);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_pair(a_dst + j * (64 * BK * 2), &maps.a[seg], lbar, m0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(a_dst, &maps.a[seg], lbar, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              if (j < p.b_boxes)
+                tma_load_2d_pair(b_dst + j * (64 * BK * 2), &maps.b[seg], lbar, n0 + 64 * j, k0);
+          } else {
+            tma_load_2d_pair(b_dst, &maps.b[seg], lbar, k0, n0);
+          }
+        }
+        __syncwarp();
+        if (++kb_in_seg >= p.kblocks[seg] && seg < p.nseg - 1) {
+          kb_in_seg = 0;
+          ++seg;
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t it = 0;
     for (int u = unit0; u < num_units; u += unit_step) {
@@ -784,9 +883,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
     uint32_t it = 0, tl = 0;
-    for (int u = unit0; u < num_units; u += unit_step, ++tl) {
+    for (int u = unit0; (!PAIR || rank == 0) && u < num_units; u += unit_step, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(tempty_bar(acc), aph ^ 1u, 12);  // epilogue has drained this accumulator
       tcgen05_fence_after();
@@ -803,11 +902,17 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = p.adesc_hi | (uint64_t)(((a_src + k * p.a_kstep) & 0x3FFFFu) >> 4);
             const uint64_t bdesc = p.bdesc_hi | (uint64_t)(((b_src + k * p.b_kstep) & 0x3FFFFu) >> 4);
-            umma_bf16(d_tmem, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          if (CLUSTER == 2) umma_commit_mc(empty_bar(s), (uint16_t)3);
-          else umma_commit(empty_bar(s));
-          if (i == nkb - 1) umma_commit(tfull_bar(acc));
+          if (PAIR) {
+            umma_commit_pair(empty_bar(s), (uint16_t)3);  // both CTAs may refill the stage
+            if (i == nkb - 1) umma_commit_pair(tfull_bar(acc), (uint16_t)3);
+          } else {
+            if (CLUSTER == 2) umma_commit_mc(empty_bar(s), (uint16_t)3);
+            else umma_commit(empty_bar(s));
+            if (i == nkb - 1) umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
       }
@@ -839,7 +944,10 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
   tcgen05_fence_before();
@@ -847,9 +955,14 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   // no CTA may leave while its peer can still multicast into its smem / arrive on its barriers
   if (CLUSTER == 2) cluster_sync_all();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
-                 "r"(TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                   "r"(TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc),
+                   "r"(TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -1027,19 +1140,22 @@ static int launch_major(const TmaMaps& maps, const GemmParams& p, dim3 grid, boo
   return launch_cfg<BN, STAGES, true, false>(maps, p, grid, st);
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+template <int BN, int STAGES, int EPI_WARPS, bool PAIR = false>
 static constexpr size_t smem_bytes_persistent() {
-  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 6) + 16 +
+  return (size_t)STAGES * (BM * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + 8 * (2 * STAGES + 6) + 16 +
          EPI_WARPS * 32 * EPI_LD * 4 + 1024;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST, int CLUSTER>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST, int CLUSTER,
+          bool PAIR = false>
 static int launch_persistent_one(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
-  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, CLUSTER>;
+  auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, CLUSTER,
+                                             PAIR>;
   static bool attr_set = false;
   static int max_ctas = 0;
-  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS>();
+  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS, PAIR>();
+  static_assert(smem <= 232448, "shared memory per CTA");
   constexpr int threads = 64 + 32 * EPI_WARPS;
   if (!attr_set) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1083,9 +1199,18 @@ static int launch_persistent_one(const TmaMaps& maps, const GemmParams& p, int m
   return 0;
 }
 
+// stages of the CTA-pair operand ring: the smem the half-width B tile frees buys depth
+template <int BN, int STAGES, int EPI_WARPS>
+static constexpr int pair_stages() {
+  return BN == 256 ? (EPI_WARPS == 8 ? 5 : 6) : STAGES;
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS = 4, bool N_FAST = false>
 static int launch_persistent_cfg(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
+  if (BN == 256 && p.cluster == 2 && p.pair)
+    return launch_persistent_one<BN, pair_stages<BN, STAGES, EPI_WARPS>(), A_MN, B_MN, MATH, EPI_WARPS,
+                                 N_FAST, 2, BN == 256>(maps, p, mt, nt, num_sms, st);
   if (p.cluster == 2)
     return launch_persistent_one<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, 2>(maps, p, mt, nt, num_sms, st);
   return launch_persistent_one<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, 1>(maps, p, mt, nt, num_sms, st);
@@ -1280,6 +1405,14 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   p.b_boxes = (bn_eff + 63) / 64;
   p.b_half_rows = bn_eff / 2;
   p.stage_tx = (unsigned)(BM * BK * 2 + (b_mn ? p.b_boxes * 64 * BK * 2 : bn_eff * BK * 2));
+  // CTA pair (tcgen05 cta_group::2): each CTA stages half of the B tile, which for an MN-major B
+  // must be whole 64-column TMA boxes
+  p.pair = (p.cluster == 2 && bn == 256 && env_int("CC_GEMM_PAIR", 1) != 0 &&
+            (b_mn ? bn_eff % 128 == 0 : bn_eff % 32 == 0)) ? 1 : 0;
+  if (p.pair) {
+    p.b_boxes = bn_eff / 128;   // per CTA
+    p.stage_tx = (unsigned)(BM * BK * 2 + (bn_eff / 2) * BK * 2);   // per CTA
+  }
 
   for (int s = 0; s < d->nseg; ++s) {
     int rc;
@@ -1313,7 +1446,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) |
             ((b_mn ? 1u : 0u) << 16) | ((uint32_t)((persistent ? bn_eff : bn) >> 3) << 17) |
-            ((uint32_t)(BM >> 4) << 24);
+            ((uint32_t)(((persistent && p.pair) ? 2 * BM : BM) >> 4) << 24);
 
   EpiParams& e = p.epi;
   e.M = d->M;

@@ -333,6 +333,51 @@ def test_effective_tile_width(bn_eff, orient, monkeypatch):
     _check(out16, ref, K, True)
 
 
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("orient", ["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("M,N,K,segs", [(300, 1000, 200, 1), (1000, 517, 2100, 1), (257, 264, 70, 1),
+                                        (640, 2300, 96, 3)])
+def test_cta_pair_mma(M, N, K, segs, orient, pair, monkeypatch):
+    """pair = "1": two SMs run one tcgen05 cta_group::2 MMA on a 256-row tile (each CTA stages
+    half of the B tile, a 6-stage operand ring); "0": the 2-CTA multicast scheme with one
+    cta_group::1 MMA per CTA.  Both against the fp32 product, and bit-identical to each other
+    (same tiles, same k order, same accumulation): all three operand-major combinations, odd
+    row-tile counts (the second CTA of the last pair idles), ragged N, a long reduction that
+    wraps the ring, and several accumulating segments."""
+    ops = _ops()
+    monkeypatch.setenv("CC_GEMM_PAIR", pair)
+    monkeypatch.setenv("CC_GEMM_BN_EFF", "256")
+    bias = torch.randn(N, device="cuda")
+    a_list, b_list, ref = [], [], 0
+    for sgi in range(segs):
+        if orient == "fwd":
+            a, b = _rand(M, K, 41 + sgi), _rand(K, N, 51 + sgi)
+            ref, am, bm = ref + a.float() @ b.float(), 0, 1
+        elif orient == "dgrad":
+            a, b = _rand(M, K, 43 + sgi), _rand(N, K, 53 + sgi)
+            ref, am, bm = ref + a.float() @ b.float().t(), 0, 0
+        else:
+            a, b = _rand(K, M, 45 + sgi), _rand(K, N, 55 + sgi)
+            ref, am, bm = ref + a.float().t() @ b.float(), 1, 1
+        a_list.append(_dev2d(a, ops))
+        b_list.append(_dev2d(b, ops))
+    out16 = ops.alloc2d(M, N)
+    out32 = ops.alloc2d(M, N, dtype=torch.float32)
+    ops.gemm(M, N, a_list, b_list, [K] * segs, am, bm, bias=bias, act=ops.ACT_SIGMOID, out16=out16,
+             out32=out32, use_ws=False)
+    torch.cuda.synchronize()
+    want = torch.sigmoid(ref + bias.cpu())
+    _check(out32, want, K * segs, False)
+    _check(out16, want, K * segs, True)
+    if pair == "1":
+        monkeypatch.setenv("CC_GEMM_PAIR", "0")
+        other = ops.alloc2d(M, N, dtype=torch.float32)
+        ops.gemm(M, N, a_list, b_list, [K] * segs, am, bm, bias=bias, act=ops.ACT_SIGMOID,
+                 out32=other, use_ws=False)
+        torch.cuda.synchronize()
+        assert torch.equal(other, out32)
+
+
 def test_effective_tile_width_auto_matches_full_width(monkeypatch):
     """The heuristic's pick (here 192 for N = 3369 at 16 row tiles) gives the same result as
     the full 256-wide tile."""
