@@ -758,8 +758,9 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      // pair: one arrival per CTA on the leader's barrier (plus the bytes of both)
-      mbar_init(full_bar(s), PAIR ? 2 : 1);
+      // pair: the leader's barrier counts its own producer and the peer's relay warp (each CTA's
+      // TMA bytes are counted on its OWN barrier; the peer forwards "my half has landed")
+      mbar_init(full_bar(s), (PAIR && rank == 0) ? 2 : 1);
       // one commit from every CTA of the cluster; pair: the leader's commit, multicast
       mbar_init(empty_bar(s), PAIR ? 1 : CLUSTER);
     }
@@ -805,24 +806,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
         if (elect_one()) {
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
-          const uint32_t lbar = mapa_cluster(full_bar(s), 0);  // the leader's barrier
           const int k0 = kb_in_seg * BK;
-          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * p.stage_tx);
-          else mbar_arrive_cluster(lbar);
+          mbar_expect_tx(full_bar(s), p.stage_tx);   // this CTA's bytes, on this CTA's barrier
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d_pair(a_dst + j * (64 * BK * 2), &maps.a[seg], lbar, m0 + 64 * j, k0);
+              tma_load_2d(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0);
           } else {
-            tma_load_2d_pair(a_dst, &maps.a[seg], lbar, k0, m0);
+            tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 128; ++j)
               if (j < p.b_boxes)
-                tma_load_2d_pair(b_dst + j * (64 * BK * 2), &maps.b[seg], lbar, n0 + 64 * j, k0);
+                tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
           } else {
-            tma_load_2d_pair(b_dst, &maps.b[seg], lbar, k0, n0);
+            tma_load_2d(b_dst, &maps.b[seg], full_bar(s), k0, n0);
           }
         }
         __syncwarp();
@@ -880,6 +879,22 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           kb_in_seg = 0;
           ++seg;
         }
+      }
+    }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===================== relay (peer CTA of a pair) =====================
+    // the peer's operands land on the peer's own barrier; this otherwise idle warp forwards
+    // each completed stage to the leader's barrier with ONE remote arrive (counting the TMA
+    // bytes of both CTAs on the leader's barrier directly -- cp.async.bulk.tensor.cta_group::2
+    // -- measured 2x slower: every response packet then updates a remote barrier)
+    uint32_t it = 0;
+    for (int u = unit0; u < num_units; u += unit_step) {
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph, 15);
+        if (lane == 0) mbar_arrive_cluster(mapa_cluster(full_bar(s), 0));
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -1522,6 +1537,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
         if (env_int("CC_GEMM_RMS_P16_TMA", 0) == 0) p.epi.rms_cs |= 2;
         // bit 2: the two epilogue warps of a lane quarter interleave their 32-column blocks
         if (env_int("CC_GEMM_RMS_INTERLEAVE", 1) != 0) p.epi.rms_cs |= 4;
+        // (the TMA-state kernels build their own instruction descriptor M from this one's)
+        p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(BM >> 4) << 24);
         // CTA pair (cta_group::2, 256-row tiles) whenever there are at least two row tiles
         if (p.cluster == 2 && env_int("CC_GEMM_RMS_PAIR", 0) != 0)
           return nfast ? launch_rms_tma<true, 2, true>(rm, p, mt, nt, g_num_sms, st)
