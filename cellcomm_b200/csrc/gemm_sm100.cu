@@ -758,9 +758,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      // pair: the leader's barrier counts its own producer and the peer's relay warp (each CTA's
-      // TMA bytes are counted on its OWN barrier; the peer forwards "my half has landed")
-      mbar_init(full_bar(s), (PAIR && rank == 0) ? 2 : 1);
+      // pair: one arrival per CTA on the leader's barrier (plus the bytes of both)
+      mbar_init(full_bar(s), PAIR ? 2 : 1);
       // one commit from every CTA of the cluster; pair: the leader's commit, multicast
       mbar_init(empty_bar(s), PAIR ? 1 : CLUSTER);
     }
@@ -806,22 +805,24 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
         if (elect_one()) {
           const uint32_t a_dst = smem_base + s * STAGE_BYTES;
           const uint32_t b_dst = a_dst + A_BYTES;
+          const uint32_t lbar = mapa_cluster(full_bar(s), 0);  // the leader's barrier
           const int k0 = kb_in_seg * BK;
-          mbar_expect_tx(full_bar(s), p.stage_tx);   // this CTA's bytes, on this CTA's barrier
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * p.stage_tx);
+          else mbar_arrive_cluster(lbar);
           if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0);
+              tma_load_2d_pair(a_dst + j * (64 * BK * 2), &maps.a[seg], lbar, m0 + 64 * j, k0);
           } else {
-            tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
+            tma_load_2d_pair(a_dst, &maps.a[seg], lbar, k0, m0);
           }
           if (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / 128; ++j)
               if (j < p.b_boxes)
-                tma_load_2d(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j, k0);
+                tma_load_2d_pair(b_dst + j * (64 * BK * 2), &maps.b[seg], lbar, n0 + 64 * j, k0);
           } else {
-            tma_load_2d(b_dst, &maps.b[seg], full_bar(s), k0, n0);
+            tma_load_2d_pair(b_dst, &maps.b[seg], lbar, k0, n0);
           }
         }
         __syncwarp();
@@ -879,22 +880,6 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           kb_in_seg = 0;
           ++seg;
         }
-      }
-    }
-  } else if (warp == 1 && PAIR && rank != 0) {
-    // ===================== relay (peer CTA of a pair) =====================
-    // the peer's operands land on the peer's own barrier; this otherwise idle warp forwards
-    // each completed stage to the leader's barrier with ONE remote arrive (counting the TMA
-    // bytes of both CTAs on the leader's barrier directly -- cp.async.bulk.tensor.cta_group::2
-    // -- measured 2x slower: every response packet then updates a remote barrier)
-    uint32_t it = 0;
-    for (int u = unit0; u < num_units; u += unit_step) {
-      for (int i = 0; i < nkb; ++i, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph, 15);
-        if (lane == 0) mbar_arrive_cluster(mapa_cluster(full_bar(s), 0));
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -1422,7 +1407,14 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   p.stage_tx = (unsigned)(BM * BK * 2 + (b_mn ? p.b_boxes * 64 * BK * 2 : bn_eff * BK * 2));
   // CTA pair (tcgen05 cta_group::2): each CTA stages half of the B tile, which for an MN-major B
   // must be whole 64-column TMA boxes
-  p.pair = (p.cluster == 2 && bn == 256 && env_int("CC_GEMM_PAIR", 1) != 0 &&
+  // Measured on B200 (profiles/r02_cta_pair_gemm_bench.json): correct in every orientation
+  // (tests/test_gemm_gpu.py::test_cta_pair_mma, bit-identical to the multicast scheme) but about
+  // half its throughput (Dx1 forward 664 vs 1,296 TFLOP/s): the MMA issuer is never stalled at
+  // issue, the operand ring is -- stage turn-around ~4 us against ~1.3 us -- and forwarding the
+  // peer's "stage landed" through a relay warp instead of remote complete_tx made it slower
+  // still, so the cost sits in the paired MMA's completion path, not in the barrier wiring.
+  // Off by default until that is understood; CC_GEMM_PAIR=1 selects it.
+  p.pair = (p.cluster == 2 && bn == 256 && env_int("CC_GEMM_PAIR", 0) != 0 &&
             (b_mn ? bn_eff % 128 == 0 : bn_eff % 32 == 0)) ? 1 : 0;
   if (p.pair) {
     p.b_boxes = bn_eff / 128;   // per CTA
