@@ -747,6 +747,7 @@ def run_record(args):
         record = rec.create_interceptor(trainer)
 
         def icpt(it, losses):
+            torch.cuda.synchronize()          # the 10 queued steps are not interceptor time
             t0 = time.perf_counter()
             _ = [float(v) for v in losses]
             record(it, losses)

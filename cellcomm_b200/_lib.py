@@ -90,6 +90,7 @@ SIGNATURES = {
     "cc_version": (C.c_int, []),
     "cc_launch_count": (C.c_longlong, []),
     "cc_arch": (C.c_char_p, []),
+    "cc_reload_env": (None, []),
     "cc_mtx_load_csr": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "cc_coo_to_csr": (C.c_int, [vp, vp, vp, c_i64, C.POINTER(vp)]),
     "cc_csr_destroy": (None, [vp]),
@@ -122,7 +123,8 @@ SIGNATURES = {
                                  c_i32, c_f32, vp, c_i64, c_i32, vp, c_i64, vp]),
     "cc_dense_wgrad": (C.c_int, [c_i32, c_i32, c_i32, vp, c_i64, vp, c_i64, vp, c_i64, c_i32, vp]),
     "cc_colsum": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, c_i32, vp]),
-    "cc_bias_grad": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp, vp, c_i64, c_i32, vp]),
+    "cc_bias_grad": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp, c_i32, vp, c_i64, c_i32,
+                               vp]),
     "cc_split_bf16": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
     "cc_dropout": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp, c_i64, c_u64, vp,
                              c_u32, c_i32, vp]),

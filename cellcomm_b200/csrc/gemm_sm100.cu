@@ -1112,6 +1112,65 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Tuning / debug knobs, read from the environment ONCE (a GEMM launch used to cost a dozen
+// getenv calls); cc_reload_env() re-reads them (tests and sweep tools change them at run time).
+struct GemmEnv {
+  int sms;
+  int bn;
+  int splits;
+  int persistent;
+  int cluster;
+  int rms_cluster;
+  int bn_eff;
+  int mn_lbo;
+  int mn_sbo;
+  int mn_kstep;
+  int k_lbo;
+  int k_sbo;
+  int rms_cs;
+  int rms_warps;
+  int rms_nfast;
+  int rms_tma;
+  int rms_p16_tma;
+  int rms_interleave;
+  int rms_pair;
+  int pair;
+};
+static GemmEnv g_env;
+static std::atomic<int> g_env_state{0};   // 0: not loaded
+static std::mutex g_env_mu;
+static int g_num_sms = 0;
+
+static const GemmEnv& gemm_env() {
+  if (g_env_state.load(std::memory_order_acquire) == 0) {
+    std::lock_guard<std::mutex> lock(g_env_mu);
+    GemmEnv e;
+    e.sms = env_int("CC_GEMM_SMS", 0);
+    e.bn = env_int("CC_GEMM_BN", 0);
+    e.splits = env_int("CC_GEMM_SPLITS", 0);
+    e.persistent = env_int("CC_GEMM_PERSISTENT", 1);
+    e.cluster = env_int("CC_GEMM_CLUSTER", 2);
+    e.rms_cluster = env_int("CC_GEMM_RMS_CLUSTER", 1);
+    e.bn_eff = env_int("CC_GEMM_BN_EFF", 0);
+    e.mn_lbo = env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
+    e.mn_sbo = env_int("CC_GEMM_MN_SBO", 1024);
+    e.mn_kstep = env_int("CC_GEMM_MN_KSTEP", UMMA_K * 128);
+    e.k_lbo = env_int("CC_GEMM_K_LBO", 16);
+    e.k_sbo = env_int("CC_GEMM_K_SBO", 1024);
+    e.rms_cs = env_int("CC_GEMM_RMS_CS", 1);
+    e.rms_warps = env_int("CC_GEMM_RMS_WARPS", 8);
+    e.rms_nfast = env_int("CC_GEMM_RMS_NFAST", -1);
+    e.rms_tma = env_int("CC_GEMM_RMS_TMA", -1);
+    e.rms_p16_tma = env_int("CC_GEMM_RMS_P16_TMA", 0);
+    e.rms_interleave = env_int("CC_GEMM_RMS_INTERLEAVE", 1);
+    e.rms_pair = env_int("CC_GEMM_RMS_PAIR", 0);
+    e.pair = env_int("CC_GEMM_PAIR", 0);
+    g_env = e;
+    g_env_state.store(1, std::memory_order_release);
+  }
+  return g_env;
+}
+
 template <int BN, int STAGES>
 static constexpr size_t smem_bytes() {
   return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 8 * (2 * STAGES + 2) + 1024;
@@ -1286,9 +1345,8 @@ static int launch_rms_tma(const RmsMaps& maps, const GemmParams& p, int mt, int 
   return 0;
 }
 
-static int g_num_sms = 0;
-
 int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
+  const GemmEnv& ENV = gemm_env();
   CC_REQUIRE(d != nullptr, "cc_gemm: null descriptor");
   CC_REQUIRE(d->M > 0 && d->N > 0, "cc_gemm: empty output %dx%d", d->M, d->N);
   CC_REQUIRE(d->nseg >= 1 && d->nseg <= MAX_SEG, "cc_gemm: nseg=%d out of range", d->nseg);
@@ -1315,12 +1373,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     CC_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     // data-parallel runs leave SMs to the NCCL kernels that overlap the backward pass: a
     // persistent GEMM launched with more CTAs than free SMs would run a second, serial wave
-    const int cap = env_int("CC_GEMM_SMS", 0);
+    const int cap = ENV.sms;
     if (cap >= 2 && cap < g_num_sms) g_num_sms = cap / 2 * 2;
   }
   const bool a_mn = d->a_mn_major != 0, b_mn = d->b_mn_major != 0;
 
-  int bn = d->force_bn ? d->force_bn : env_int("CC_GEMM_BN", 0);
+  int bn = d->force_bn ? d->force_bn : ENV.bn;
   if (bn == 0) bn = (d->N > 128) ? 256 : 128;
   CC_REQUIRE(bn == 128 || bn == 256, "cc_gemm: BN=%d unsupported", bn);
 
@@ -1342,7 +1400,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   int splits = 1;
   const long long Mpad = (long long)mt * BM, Npad = (long long)nt * bn;
   if (d->workspace != nullptr && d->rms_p32 == nullptr) {
-    int want = d->force_splits ? d->force_splits : env_int("CC_GEMM_SPLITS", 0);
+    int want = d->force_splits ? d->force_splits : ENV.splits;
     if (want == 0) {
       // split-K only when the tile grid leaves more than half of the SMs idle (small batch,
       // long reduction: the weight-streaming regime of the reference's batch 128); otherwise
@@ -1372,19 +1430,19 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     splits = 1;
   }
   const bool persistent =
-      splits == 1 && (env_int("CC_GEMM_PERSISTENT", 1) != 0 || d->rms_p32 != nullptr ||
+      splits == 1 && (ENV.persistent != 0 || d->rms_p32 != nullptr ||
                       d->route_world > 0);
 
   // 2-CTA clusters (B tile multicast) whenever there are at least two row tiles
-  p.cluster = (persistent && mt >= 2 && env_int("CC_GEMM_CLUSTER", 2) == 2 &&
-               (d->rms_p32 == nullptr || env_int("CC_GEMM_RMS_CLUSTER", 1) != 0)) ? 2 : 1;
+  p.cluster = (persistent && mt >= 2 && ENV.cluster == 2 &&
+               (d->rms_p32 == nullptr || ENV.rms_cluster != 0)) ? 2 : 1;
   // effective tile width of the persistent kernel: the candidate that minimises
   // waves x (per-tile cost); e.g. N = 3369 at batch 2048 is 224 tiles of 256 (1.51 waves on 148
   // SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each shorter).  The per-tile cost model is
   // operand bytes (A is fixed, B scales with the width): the kernels are L2->SM bound.
   int bn_eff = bn;
   if (persistent && bn == 256 && d->rms_p32 == nullptr) {
-    const int forced = env_int("CC_GEMM_BN_EFF", 0);
+    const int forced = ENV.bn_eff;
     if (forced >= 32 && forced <= 256 && forced % 32 == 0) {
       bn_eff = forced;
     } else {
@@ -1414,7 +1472,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // peer's "stage landed" through a relay warp instead of remote complete_tx made it slower
   // still, so the cost sits in the paired MMA's completion path, not in the barrier wiring.
   // Off by default until that is understood; CC_GEMM_PAIR=1 selects it.
-  p.pair = (p.cluster == 2 && bn == 256 && env_int("CC_GEMM_PAIR", 0) != 0 &&
+  p.pair = (p.cluster == 2 && bn == 256 && ENV.pair != 0 &&
             (b_mn ? bn_eff % 128 == 0 : bn_eff % 32 == 0)) ? 1 : 0;
   if (p.pair) {
     p.b_boxes = bn_eff / 128;   // per CTA
@@ -1440,11 +1498,11 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // K advance = 32 B inside the swizzle row.  MN-major, 128B swizzle: 64-element MN atoms are
   // separate TMA boxes 64*BK*2 = 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance =
   // 16 rows * 128 B.
-  const uint32_t mn_lbo = (uint32_t)env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
-  const uint32_t mn_sbo = (uint32_t)env_int("CC_GEMM_MN_SBO", 1024);
-  const uint32_t mn_kstep = (uint32_t)env_int("CC_GEMM_MN_KSTEP", UMMA_K * 128);
-  const uint32_t k_lbo = (uint32_t)env_int("CC_GEMM_K_LBO", 16);
-  const uint32_t k_sbo = (uint32_t)env_int("CC_GEMM_K_SBO", 1024);
+  const uint32_t mn_lbo = (uint32_t)ENV.mn_lbo;
+  const uint32_t mn_sbo = (uint32_t)ENV.mn_sbo;
+  const uint32_t mn_kstep = (uint32_t)ENV.mn_kstep;
+  const uint32_t k_lbo = (uint32_t)ENV.k_lbo;
+  const uint32_t k_sbo = (uint32_t)ENV.k_sbo;
   p.adesc_hi = a_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
   p.bdesc_hi = b_mn ? desc_hi(mn_lbo, mn_sbo) : desc_hi(k_lbo, k_sbo);
   p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
@@ -1479,7 +1537,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.rms_rho = d->rms_rho;
   e.rms_momentum = d->rms_momentum;
   e.rms_eps = d->rms_eps;
-  e.rms_cs = env_int("CC_GEMM_RMS_CS", 1);
+  e.rms_cs = ENV.rms_cs;
   e.route_world = d->route_world;
   e.route_shard = (unsigned)d->route_shard;
   e.route_off0 = d->route_off0;
@@ -1491,18 +1549,18 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     // epilogue streams 26 B per element, so it gets 8 warps (twice the loads in flight) and
     // the main loop one stage less
     if (bn == 256 && d->rms_p32 != nullptr && a_mn && b_mn && d->alpha == 1.f &&
-        d->bias == nullptr && d->act == 0 && e.dact == 0 && env_int("CC_GEMM_RMS_WARPS", 8) == 8) {
+        d->bias == nullptr && d->act == 0 && e.dact == 0 && ENV.rms_warps == 8) {
       // raster: walk along N (DRAM-page-local optimiser stream) when the whole B operand
       // (dZ, batch x N) stays L2-resident across row blocks; otherwise keep m fastest so the
       // CTAs of a wave share one B tile and A (X^T) is the L2-resident operand
-      int nfast = env_int("CC_GEMM_RMS_NFAST", -1);
+      int nfast = ENV.rms_nfast;
       if (nfast < 0) nfast = ((long long)total * BK * d->N * 2 <= (48ll << 20)) ? 1 : 0;
       // optimiser state moved by TMA (wgrad_rmsprop_kernel.cuh) whenever the parameter block is
       // TMA-addressable: 16-byte aligned bases and row pitch
       // (measured, profiles/r02_fused_rmsprop_tma_sweep.jsonl: ahead of the register epilogue
       // while the batch reduction is short -- the reference's batch 128 -- and behind it when
       // the operand ring is long, so the default follows the number of k-blocks)
-      int use_tma = env_int("CC_GEMM_RMS_TMA", -1);
+      int use_tma = ENV.rms_tma;
       if (use_tma < 0) use_tma = total <= 4 ? 1 : 0;
       const bool tma_ok =
           use_tma != 0 && (d->rms_ld & 7) == 0 && d->beta32 == 0 &&
@@ -1526,13 +1584,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
                              (uint64_t)d->rms_ld, 32, 32, MAP_BF16_SW64);
         if (rc) return rc;
         // bit 1: bf16 weight copy written by row stores from registers instead of a TMA store
-        if (env_int("CC_GEMM_RMS_P16_TMA", 0) == 0) p.epi.rms_cs |= 2;
+        if (ENV.rms_p16_tma == 0) p.epi.rms_cs |= 2;
         // bit 2: the two epilogue warps of a lane quarter interleave their 32-column blocks
-        if (env_int("CC_GEMM_RMS_INTERLEAVE", 1) != 0) p.epi.rms_cs |= 4;
+        if (ENV.rms_interleave != 0) p.epi.rms_cs |= 4;
         // (the TMA-state kernels build their own instruction descriptor M from this one's)
         p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(BM >> 4) << 24);
         // CTA pair (cta_group::2, 256-row tiles) whenever there are at least two row tiles
-        if (p.cluster == 2 && env_int("CC_GEMM_RMS_PAIR", 0) != 0)
+        if (p.cluster == 2 && ENV.rms_pair != 0)
           return nfast ? launch_rms_tma<true, 2, true>(rm, p, mt, nt, g_num_sms, st)
                        : launch_rms_tma<false, 2, true>(rm, p, mt, nt, g_num_sms, st);
         if (p.cluster == 2)
@@ -1568,6 +1626,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
 }
 
 }  // namespace cc
+
+extern "C" void cc_reload_env(void) {
+  std::lock_guard<std::mutex> lock(cc::g_env_mu);
+  cc::g_env_state.store(0, std::memory_order_release);
+  cc::g_num_sms = 0;
+}
 
 extern "C" int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream) {
   return cc::gemm_impl(desc, (cudaStream_t)stream);

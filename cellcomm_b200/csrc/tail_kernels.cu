@@ -726,16 +726,18 @@ extern "C" int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, 
 }
 
 extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
-                            int64_t cols, int32_t act, float* out, void* dz, int64_t lddz,
-                            int32_t dtypes, cc_stream_t stream) {
+                            int64_t cols, int32_t act, float* out, int32_t beta, void* dz,
+                            int64_t lddz, int32_t dtypes, cc_stream_t stream) {
   if (cols <= 0) return 0;
   if (rows <= 0) {
-    fill_f32_kernel<<<ew_grid(cols, 256), 256, 0, ST(stream)>>>(out, 0.f, cols);
-    CC_CHECK_LAUNCH();
+    if (!beta) {
+      fill_f32_kernel<<<ew_grid(cols, 256), 256, 0, ST(stream)>>>(out, 0.f, cols);
+      CC_CHECK_LAUNCH();
+    }
     return 0;
   }
   return launch_colreduce<3>(mat(dy, lddy, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), rows, cols,
-                             nullptr, nullptr, out, 0, ST(stream), act,
+                             nullptr, nullptr, out, beta, ST(stream), act,
                              mat(dz, lddz, F32(dtypes, 2)));
 }
 

@@ -902,6 +902,10 @@ class Net:
         if train and self._bucketed():
             for bk in self.buckets:
                 bk["pending"], bk["launched"] = bk["pieces"], False
+        if train and self.n_flat > self.small_off:
+            # ONE fill for every bias gradient of the network (they lie contiguously behind the
+            # kernels in the flat gradient buffer); the per-layer reductions then accumulate
+            ops.fill_f32(self.g32[self.small_off:], 0.0)
 
         out_t = g.output
         seed = self._buf(self.grad, out_t)[:rows]
@@ -932,7 +936,7 @@ class Net:
                     dzs = [dz, dz_lo]
                 elif train:
                     # one pass over dy and y: dz for the GEMMs and the bias gradient
-                    ops.bias_grad(dy, A[out], act, L["db"], dz=dz)
+                    ops.bias_grad(dy, A[out], act, L["db"], dz=dz, beta=1)
                     dzs = [dz]
                 else:
                     ops.act_bwd(dy, A[out], dz, act)
@@ -980,7 +984,7 @@ class Net:
                     ro += k
                 if train:
                     if out in self.prebn:
-                        ops.bias_grad(dy, A[out], 0, L["db"])     # dy already holds dz (fp32)
+                        ops.bias_grad(dy, A[out], 0, L["db"], beta=1)   # dy already holds dz (fp32)
                     # (other layers: done together with dz above)
                     if self.fuse_optimizer and "w16lo" in L:
                         # the wgrad epilogues above just updated this kernel: new low-order term

@@ -75,6 +75,11 @@ def launch_count():
     return int(_lib.load().cc_launch_count())
 
 
+def reload_env():
+    """Make the library re-read its CC_GEMM_* environment knobs (it reads them once)."""
+    _lib.load().cc_reload_env()
+
+
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
          alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
@@ -234,13 +239,13 @@ def colsum(x, out32, beta=0):
                                 _mask(x), _stream()))
 
 
-def bias_grad(dy, y, act, out32, dz=None):
-    """out32[c] = sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient);
+def bias_grad(dy, y, act, out32, dz=None, beta=0):
+    """out32[c] (+)= sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient);
     dz (optional): also store dy * act'(y) there (one pass instead of act_bwd + bias_grad)."""
     _req(out32, torch.float32, "out")
     check(_lib.load().cc_bias_grad(_p(dy), _ld(dy), _p(y), _ld(y), dy.shape[0], dy.shape[1],
-                                   int(act), _p(out32), _p(dz), _ld(dz), _mask(dy, y, dz),
-                                   _stream()))
+                                   int(act), _p(out32), int(beta), _p(dz), _ld(dz),
+                                   _mask(dy, y, dz), _stream()))
 
 
 def split_bf16(x, hi, lo):

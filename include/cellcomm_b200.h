@@ -39,6 +39,10 @@ int cc_version(void);
 long long cc_launch_count(void);
 /* compiled-for architecture string, e.g. "sm_100a" */
 const char* cc_arch(void);
+/* The library reads its tuning / debug environment variables (CC_GEMM_*) once, at the first
+ * cc_gemm call; this makes the next call read them again (tests and sweep tools that change
+ * them at run time). */
+void cc_reload_env(void);
 
 /* ------------------------------------------------- loader (host, no GPU)
  * replaces: load_matrix()  src/cell_type_training.py:9-17
@@ -214,10 +218,11 @@ int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
  * (Summing the bf16 dZ instead loses the near-cancelling sums of biases that feed a
  * BatchNormalization.)  dz (optional, NULL to skip): also write dz[r,c] = dy*act'(y), the
  * operand of the wgrad / dgrad GEMMs, in the same pass (replaces a cc_act_bwd launch for
- * trained layers).  dtypes: dy, y, dz */
+ * trained layers).  beta != 0: out += the sums (the caller zeroed a whole bias region with one
+ * fill instead of one per layer).  dtypes: dy, y, dz */
 int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
-                 int64_t cols, int32_t act, float* out, void* dz, int64_t lddz, int32_t dtypes,
-                 cc_stream_t stream);
+                 int64_t cols, int32_t act, float* out, int32_t beta, void* dz, int64_t lddz,
+                 int32_t dtypes, cc_stream_t stream);
 /* hi = bf16(x), lo = bf16(x - hi): two-term bf16 expansion of an activation, fed to cc_gemm
  * as two accumulating segments where 8 mantissa bits are too few.  dtypes: x */
 int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo, int64_t ldlo,

@@ -80,6 +80,10 @@ def test_product_run_two_gpus_equals_one_gpu(tmp_path):
     assert a["enc"].shape == b["enc"].shape == (301, 3)
     # iteration 0's recorded encodings come after 2 steps on each side; iteration 1's after 4
     assert np.abs(np.array(a["xs"][0]) - np.array(b["xs"][0])).max() <= 255 * 5e-2
-    # the sharded run's checkpoint holds every rank's optimiser state, not rank 0's shard only
-    assert b["rms_nonzero"] and min(b["rms_nonzero"].values()) > 0.9, b["rms_nonzero"]
+    # the sharded run's checkpoint holds every rank's optimiser state, not rank 0's shard only:
+    # every big rms slot is as densely populated as in the 1-GPU run (a slot that only held rank
+    # 0's shard would be half zeros; dead ReLU columns are zero in both runs alike)
+    assert b["rms_nonzero"] and set(a["rms_nonzero"]) == set(b["rms_nonzero"])
+    for k, frac in a["rms_nonzero"].items():
+        assert abs(b["rms_nonzero"][k] - frac) <= 0.05, (k, frac, b["rms_nonzero"][k])
     print("captured data-parallel step graphs on rank 0:", b["graphs"])

@@ -45,6 +45,7 @@ for (K, N) in ((6738, 33694), (33694, 10108)):
             os.environ["CC_GEMM_RMS_NFAST"] = str(nfast)
             os.environ["CC_GEMM_RMS_CS"] = str(cs)
             os.environ["CC_GEMM_RMS_PREFETCH"] = str(pf)
+            ops.reload_env()
             tf = timeit(lambda: ops.dense_wgrad(x, dz, None, rms=rms))
             emit({"K": K, "N": N, "batch": B, "kernel": "wgrad+fused rmsprop", "nfast": nfast,
                   "cs": cs, "prefetch": pf, "ms": tf, "GB/s": 26.0 * K * N / tf / 1e6,

@@ -27,6 +27,7 @@ for (K, N) in ((6738, 33694), (33694, 10108), (3369, 6738)):
             os.environ["CC_GEMM_RMS_PAIR"] = str(pair)
             os.environ["CC_GEMM_RMS_INTERLEAVE"] = str(inter)
             os.environ["CC_GEMM_RMS_NFAST"] = str(nfast)
+            ops.reload_env()
             t = timeit(lambda: ops.dense_wgrad(x, dz, None, rms=rms))
             rec = {"K": K, "N": N, "batch": B, "tma_state": tma, "pair": pair, "interleave": inter,
                    "nfast": nfast, "ms": t, "GB/s": 26.0 * K * N / t / 1e6}
