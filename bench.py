@@ -493,14 +493,10 @@ def run_ours(args):
     r0, r1 = rank * shard, min(args.cells, (rank + 1) * shard)
     enc_out = torch.empty((r1 - r0, Z), dtype=torch.float32, device=dev)
     tile_rows = args.encode_tile
-    tile = ops.alloc2d(tile_rows, args.genes, device=dev)
 
     def encode_shard():
-        for s in range(r0, r1, tile_rows):
-            m = min(tile_rows, r1 - s)
-            ops.gather_rows(rowptr, colidx, values, args.genes, row_start=s, n_rows=m,
-                            out16=tile[:m])
-            e.encode(tile[:m], out32=enc_out[s - r0:s - r0 + m])
+        # cc_encode_stream: this rank's rows in one C call (gather + encoder forward per tile)
+        e.encode_stream(rowptr, colidx, values, r0, r1, enc_out, tile_rows=tile_rows)
 
     encode_shard()
     barrier()
@@ -853,20 +849,18 @@ def run_encode(args):
     colidx = np.tile(ci, reps)[:rowptr[-1]]
     values = np.tile(va, reps)[:rowptr[-1]]
     data = CellMatrix(rowptr, colidx, values, np.arange(1, n_local + 1), np.arange(1, args.genes + 1))
-    net = ContinuousCellBiGan(Z, gene_size=args.genes)
+    # every rank holds (only) its own row shard: the network is built without a process group,
+    # so encoding_prediction(data) is this rank's pass over its shard -- no communication
+    from cellcomm_b200 import engine as eng
+    net = ContinuousCellBiGan(Z, gene_size=args.genes, dist=eng._NoDist())
     e = net._engine
     d_rowptr, d_colidx, d_values = data.device_csr(dev)
     tile_rows = args.encode_tile
-    tile = ops.alloc2d(tile_rows, args.genes, device=dev)
     out = torch.empty((n_local, Z), dtype=torch.float32, device=dev)
-    e.reserve(tile_rows)
 
     def one_pass():
-        for s_ in range(0, n_local, tile_rows):
-            m = min(tile_rows, n_local - s_)
-            ops.gather_rows(d_rowptr, d_colidx, d_values, args.genes, row_start=s_, n_rows=m,
-                            out16=tile[:m])
-            e.encode(tile[:m], out32=out[s_:s_ + m])
+        # cc_encode_stream: gather + encoder forward, tile by tile, ONE C call per pass
+        e.encode_stream(d_rowptr, d_colidx, d_values, 0, n_local, out, tile_rows=tile_rows)
 
     steps, warm = max(1, args.steps), max(3, args.warmup)
     one_pass()
