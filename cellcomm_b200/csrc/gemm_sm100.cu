@@ -281,6 +281,16 @@ __device__ __forceinline__ void for_each_valid(float4 (&g)[8], int nrow, int nco
   }
 }
 
+// evict-first 16-byte load that asks L2 to fetch the whole 256-byte neighbourhood from DRAM:
+// the lane's next 32-column block of the same rows lies in it
+__device__ __forceinline__ float4 ldcs_256(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cs.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
 template <bool MATH>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage /*32x36*/, int lane,
                                                int r0, int c0, const uint32_t (&raw)[32]) {
@@ -348,7 +358,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
       for (int t = 0; t < 8; ++t) {
         if (t < nrow) {
           const long long off = off0 + t * step;
-          if (e.rms_cs) {
+          if (e.rms_cs & 8) {
+            w[t] = ldcs_256(e.rms_p32 + off);
+            s[t] = ldcs_256(e.rms_ms + off);
+            m[t] = ldcs_256(e.rms_mom + off);
+          } else if (e.rms_cs & 1) {
             w[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_p32 + off));
             s[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_ms + off));
             m[t] = __ldcs(reinterpret_cast<const float4*>(e.rms_mom + off));
@@ -378,7 +392,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
           ww.y = w[t].y - mm.y;
           ww.z = w[t].z - mm.z;
           ww.w = w[t].w - mm.w;
-          if (e.rms_cs) {
+          if (e.rms_cs & 1) {
             __stcs(reinterpret_cast<float4*>(e.rms_ms + off), ss);
             __stcs(reinterpret_cast<float4*>(e.rms_mom + off), mm);
             __stcs(reinterpret_cast<float4*>(e.rms_p32 + off), ww);
@@ -1040,7 +1054,8 @@ struct MapKeyHash {
 enum MapKind : uint32_t {
   MAP_BF16_SW128 = 0,   // GEMM operands
   MAP_F32_SW128 = 1,    // optimiser state blocks (32 fp32 = one 128-byte swizzle row)
-  MAP_BF16_SW64 = 2     // bf16 weight copy blocks (32 bf16 = one 64-byte swizzle row)
+  MAP_BF16_SW64 = 2,    // bf16 weight copy blocks (32 bf16 = one 64-byte swizzle row)
+  MAP_F32_SW128_L2_256 = 3   // state blocks fetched from DRAM in 256-byte pieces
 };
 
 // Row-major [outer, inner] tensor with leading dimension ld (elements).
@@ -1057,7 +1072,8 @@ static int make_map_kind(CUtensorMap* out, const void* ptr, uint64_t inner, uint
       return 0;
     }
   }
-  const uint64_t esize = kind == MAP_F32_SW128 ? 4 : 2;
+  const bool f32 = kind == MAP_F32_SW128 || kind == MAP_F32_SW128_L2_256;
+  const uint64_t esize = f32 ? 4 : 2;
   PFN_encodeTiled enc = get_encode_fn();
   CC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   CC_REQUIRE(((uintptr_t)ptr & 15) == 0, "cc_gemm: operand base %p is not 16-byte aligned", ptr);
@@ -1069,13 +1085,13 @@ static int make_map_kind(CUtensorMap* out, const void* ptr, uint64_t inner, uint
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out,
-                   kind == MAP_F32_SW128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                         : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                    2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    kind == MAP_BF16_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   kind == MAP_BF16_SW128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   (kind == MAP_BF16_SW128 || kind == MAP_F32_SW128_L2_256)
+                       ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                       : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CC_REQUIRE(r == CUDA_SUCCESS,
              "cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u",
@@ -1135,6 +1151,7 @@ struct GemmEnv {
   int rms_interleave;
   int rms_pair;
   int pair;
+  int rms_l2_256;
 };
 static GemmEnv g_env;
 static std::atomic<int> g_env_state{0};   // 0: not loaded
@@ -1165,6 +1182,7 @@ static const GemmEnv& gemm_env() {
     e.rms_interleave = env_int("CC_GEMM_RMS_INTERLEAVE", 1);
     e.rms_pair = env_int("CC_GEMM_RMS_PAIR", 0);
     e.pair = env_int("CC_GEMM_PAIR", 0);
+    e.rms_l2_256 = env_int("CC_GEMM_RMS_L2_256", 0);
     g_env = e;
     g_env_state.store(1, std::memory_order_release);
   }
@@ -1537,7 +1555,9 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.rms_rho = d->rms_rho;
   e.rms_momentum = d->rms_momentum;
   e.rms_eps = d->rms_eps;
-  e.rms_cs = ENV.rms_cs;
+  // bit 0: evict-first hints on the optimiser-state stream; bit 3: 256-byte L2 fetch granularity
+  // for its loads (bits 1, 2: see the TMA-state epilogue below)
+  e.rms_cs = (ENV.rms_cs ? 1 : 0) | (ENV.rms_l2_256 ? 8 : 0);
   e.route_world = d->route_world;
   e.route_shard = (unsigned)d->route_shard;
   e.route_off0 = d->route_off0;
@@ -1573,12 +1593,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
           rm.a[s] = maps.a[s];
           rm.b[s] = maps.b[s];
         }
+        const MapKind sk = ENV.rms_l2_256 ? MAP_F32_SW128_L2_256 : MAP_F32_SW128;
         int rc = make_map_kind(&rm.p32, d->rms_p32, (uint64_t)d->N, (uint64_t)d->M,
-                               (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+                               (uint64_t)d->rms_ld, 32, 32, sk);
         if (!rc) rc = make_map_kind(&rm.ms, d->rms_ms, (uint64_t)d->N, (uint64_t)d->M,
-                                    (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+                                    (uint64_t)d->rms_ld, 32, 32, sk);
         if (!rc) rc = make_map_kind(&rm.mom, d->rms_mom, (uint64_t)d->N, (uint64_t)d->M,
-                                    (uint64_t)d->rms_ld, 32, 32, MAP_F32_SW128);
+                                    (uint64_t)d->rms_ld, 32, 32, sk);
         if (!rc && d->rms_p16 != nullptr)
           rc = make_map_kind(&rm.p16, d->rms_p16, (uint64_t)d->N, (uint64_t)d->M,
                              (uint64_t)d->rms_ld, 32, 32, MAP_BF16_SW64);

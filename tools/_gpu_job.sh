@@ -1,4 +1,6 @@
-python -m pytest tests -m gpu -q --tb=short --maxfail=30 --durations=8 > gpurun_out/r2_tests7.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests7.log
-python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_smoke7.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2_tests7.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench7.json 2> gpurun_out/r2_bench7.err; echo "bench rc=$?" >> gpurun_out/r2_tests7.log
-tail -n 6 gpurun_out/r2_tests7.log
+python tools/rms_tma_bench.py gpurun_out/r2_rms_l2_256.jsonl > gpurun_out/r2_rms_l2_256.log 2>&1; echo "rc=$?"
+python - <<'P'
+import json
+for l in open('gpurun_out/r2_rms_l2_256.jsonl'):
+    r=json.loads(l); print(r['K'],r['N'],r['batch'],'tma',r['tma_state'],'il',r['interleave'],'l2',r['l2_256'],round(r['ms'],3),round(r['GB/s']))
+P

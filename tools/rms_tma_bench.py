@@ -21,8 +21,9 @@ for (K, N) in ((6738, 33694), (33694, 10108), (3369, 6738)):
     for B in (128, 2048):
         x = ops.alloc2d(B, K); x.normal_()
         dz = ops.alloc2d(B, N); dz.normal_(std=1e-3)
-        for tma, pair, inter, nfast in ((0, 0, 0, -1), (1, 0, 0, -1), (1, 0, 1, -1), (1, 1, 0, -1),
-                                        (1, 1, 1, -1), (1, 1, 1, 0), (1, 1, 1, 1)):
+        for tma, pair, inter, nfast, l2 in ((0, 0, 0, -1, 0), (0, 0, 0, -1, 1), (1, 0, 1, -1, 0),
+                                            (1, 0, 1, -1, 1), (1, 0, 0, -1, 1)):
+            os.environ["CC_GEMM_RMS_L2_256"] = str(l2)
             os.environ["CC_GEMM_RMS_TMA"] = str(tma)
             os.environ["CC_GEMM_RMS_PAIR"] = str(pair)
             os.environ["CC_GEMM_RMS_INTERLEAVE"] = str(inter)
@@ -30,7 +31,7 @@ for (K, N) in ((6738, 33694), (33694, 10108), (3369, 6738)):
             ops.reload_env()
             t = timeit(lambda: ops.dense_wgrad(x, dz, None, rms=rms))
             rec = {"K": K, "N": N, "batch": B, "tma_state": tma, "pair": pair, "interleave": inter,
-                   "nfast": nfast, "ms": t, "GB/s": 26.0 * K * N / t / 1e6}
+                   "nfast": nfast, "l2_256": l2, "ms": t, "GB/s": 26.0 * K * N / t / 1e6}
             print(json.dumps(rec), flush=True)
             if out:
                 out.write(json.dumps(rec) + "\n")
