@@ -806,7 +806,10 @@ class Net:
                                 segs.append((terms[0], ro, wlo))
                                 second += [(t, ro, wlo) for t in terms[1:]]
                         ro += g.widths[i]
-                    if len(segs) + len(second) <= 4:     # CC_GEMM_MAX_SEG
+                    # (second-order terms, 2^-16 relative, only where arithmetic is emulated
+                    # exactly: the host-logic tests compare at 1e-4; on the GPU they would cost
+                    # a fourth GEMM segment for less than the bf16 rounding of everything else)
+                    if second and self.device.type != "cuda" and len(segs) + len(second) <= 4:
                         segs += second
                     xs, offs, ws = ([sg[j] for sg in segs] for j in range(3))
                     if xs:
@@ -951,8 +954,9 @@ class Net:
                             wseg = L["w16"][ro:ro + k]
                             dst = self._buf(self.grad, i)[:rows]
                             d_terms, w_terms = list(dzs), [wseg] * len(dzs)
-                            if "w16lo" in L:         # dz_hi @ W_lo^T (+ dz_lo @ W_lo^T)
-                                for d_ in dzs[:4 - len(dzs)]:
+                            if "w16lo" in L:         # dz_hi @ W_lo^T (+ dz_lo @ W_lo^T, see forward)
+                                n_lo = 1 if self.device.type == "cuda" else 4 - len(dzs)
+                                for d_ in dzs[:n_lo]:
                                     d_terms.append(d_)
                                     w_terms.append(L["w16lo"][ro:ro + k])
                             ops.dense_dgrad(d_terms, w_terms, dst, beta=1 if state[i] else 0)

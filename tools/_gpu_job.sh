@@ -1,12 +1,6 @@
-N=${1:-8}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-L=gpurun_out/r2_n${N}.log; : > $L
-if [ "$N" = "8" ]; then
-CELLCOMM_DP_LOG=gpurun_out/r2_dp_check_n8.jsonl python -m pytest tests/test_data_parallel_gpu.py -m gpu -q --tb=short -k "hardware and 8" > gpurun_out/r2_dp_tests_n8.log 2>&1; echo "dp pytest rc=$?" >> $L
-$TR --master-port 29521 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_train_n$N.json 2> gpurun_out/r2_bench_train_n$N.err; echo "train rc=$?" >> $L
-$TR --master-port 29522 bench.py --workload record --gpus $N --steps 2 --warmup 1 > gpurun_out/r2_bench_record_n$N.json 2> gpurun_out/r2_bench_record_n$N.err; echo "record rc=$?" >> $L
-$TR --master-port 29523 bench.py --gpus $N --steps 10 --warmup 3 --strong --batch 2048 --no-roofline > gpurun_out/r2_bench_strong_n$N.json 2> gpurun_out/r2_bench_strong_n$N.err; echo "strong rc=$?" >> $L
-fi
-$TR --master-port 29524 bench.py --workload classify --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_classify_n$N.json 2> gpurun_out/r2_bench_classify_n$N.err; echo "classify rc=$?" >> $L
-$TR --master-port 29525 bench.py --workload encode --gpus $N --steps 3 --warmup 3 > gpurun_out/r2_bench_encode_n$N.json 2> gpurun_out/r2_bench_encode_n$N.err; echo "encode rc=$?" >> $L
-cat $L
+rm -f gpurun_out/parity_r2b.jsonl
+CELLCOMM_PARITY_LOG=gpurun_out/parity_r2b.jsonl python -m pytest tests/test_parity_gpu.py tests/test_parity_baseline_shape_gpu.py -m gpu -q --tb=short > gpurun_out/r2_tests8.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests8.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench8.json 2> gpurun_out/r2_bench8.err; echo "bench rc=$?" >> gpurun_out/r2_tests8.log
+CMD="python bench.py --steps 2 --warmup 3 --graph 0 --no-cpu-baseline --small-batch 0 --dense-e2e-steps 0 --no-roofline"
+$CMD > gpurun_out/r2_plain_launches.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --kernel-name-base demangled -k regex:cc:: -s 1700 -c 2600 --csv --log-file gpurun_out/r2_ncu_launches_b2048.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1; echo "ncu rc=$?" >> gpurun_out/r2_tests8.log
+tail -n 5 gpurun_out/r2_tests8.log
