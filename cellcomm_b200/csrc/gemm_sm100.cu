@@ -1425,7 +1425,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       // the persistent kernel runs the tiles unsplit
       const int tiles = mt * nt;
       if (2 * tiles <= g_num_sms && total >= 8) {
-        want = (2 * g_num_sms + tiles - 1) / tiles;
+        // as many splits as keep every CTA in ONE co-resident wave (2 CTAs per SM): rounding up
+        // here put 4-8 % of the CTAs into a second wave and nearly doubled the launch time of
+        // the weight-streaming GEMMs (Dx1 forward at batch 128: 40 tiles x 8 splits = 320 CTAs
+        // on 296 slots)
+        want = (2 * g_num_sms) / tiles;
+        if (want < 1) want = 1;
         if (want > total / 4) want = total / 4;
       } else {
         want = 1;
