@@ -123,8 +123,8 @@ SIGNATURES = {
                                  c_i32, c_f32, vp, c_i64, c_i32, vp, c_i64, vp]),
     "cc_dense_wgrad": (C.c_int, [c_i32, c_i32, c_i32, vp, c_i64, vp, c_i64, vp, c_i64, c_i32, vp]),
     "cc_colsum": (C.c_int, [vp, c_i64, c_i64, c_i64, vp, c_i32, c_i32, vp]),
-    "cc_bias_grad": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp, c_i32, vp, c_i64, c_i32,
-                               vp]),
+    "cc_bias_grad": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp, c_i32, vp, c_i64, vp,
+                               c_i64, c_i32, vp]),
     "cc_split_bf16": (C.c_int, [vp, c_i64, vp, c_i64, vp, c_i64, c_i64, c_i64, c_i32, vp]),
     "cc_dropout": (C.c_int, [vp, c_i64, vp, c_i64, c_i64, c_i64, c_f32, vp, c_i64, c_u64, vp,
                              c_u32, c_i32, vp]),

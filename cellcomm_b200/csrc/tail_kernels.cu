@@ -332,7 +332,8 @@ template <int MODE>  // 0: x (1 output)  1: x, x^2   2: dy, dy*xhat   3: dy*act'
 __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long long cols,
                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                  float* __restrict__ out, int accumulate, int act,
-                                 const Mat dz = Mat{nullptr, 0, 0}) {
+                                 const Mat dz = Mat{nullptr, 0, 0},
+                                 const Mat dzlo = Mat{nullptr, 0, 0}) {
   __shared__ float s0[8][64], s1[8][64];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const long long c = (long long)blockIdx.x * 64 + tx * 2;
@@ -373,6 +374,8 @@ __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long 
         a0 += v0;
         a1 += v1;
         if (dz.p != nullptr) store_pair(dz, r, c, c0ok, c1ok, v0, v1);
+        if (dzlo.p != nullptr)   // two-term bf16 expansion of dz: the low-order term
+          store_pair(dzlo, r, c, c0ok, c1ok, v0 - bf2f(f2bf(v0)), v1 - bf2f(f2bf(v1)));
       }
     }
   }
@@ -393,6 +396,7 @@ __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long 
         t0 += s0[y][j];
         t1 += s1[y][j];
       }
+      if (out == nullptr) continue;
       if (gridDim.y > 1 || accumulate) {
         atomicAdd(out + cc_, t0);
         if (MODE == 1 || MODE == 2) atomicAdd(out + cols + cc_, t1);
@@ -407,7 +411,8 @@ __global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long 
 template <int MODE>
 static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long long cols,
                             const float* mean, const float* rstd, float* out, int accumulate,
-                            cudaStream_t st, int act = 0, const Mat dz = Mat{nullptr, 0, 0}) {
+                            cudaStream_t st, int act = 0, const Mat dz = Mat{nullptr, 0, 0},
+                            const Mat dzlo = Mat{nullptr, 0, 0}) {
   const unsigned gx = (unsigned)((cols + 63) / 64);
   // enough row slabs to cover ~2 waves of the machine when there are few column blocks
   unsigned gy = 1;
@@ -418,13 +423,13 @@ static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long lon
     if (gy > maxy) gy = maxy;
     if (gy < 1) gy = 1;
   }
-  if (gy > 1 && !accumulate) {
+  if (gy > 1 && !accumulate && out != nullptr) {
     const long long n = ((MODE == 0 || MODE == 3) ? 1 : 2) * cols;
     fill_f32_kernel<<<ew_grid(n, 256), 256, 0, st>>>(out, 0.f, n);
     CC_CHECK_LAUNCH();
   }
   colreduce_kernel<MODE><<<dim3(gx, gy), dim3(32, 8), 0, st>>>(a, b, rows, cols, mean, rstd, out,
-                                                               accumulate, act, dz);
+                                                               accumulate, act, dz, dzlo);
   CC_CHECK_LAUNCH();
   return 0;
 }
@@ -727,10 +732,14 @@ extern "C" int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, 
 
 extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
                             int64_t cols, int32_t act, float* out, int32_t beta, void* dz,
-                            int64_t lddz, int32_t dtypes, cc_stream_t stream) {
+                            int64_t lddz, void* dz_lo, int64_t lddz_lo, int32_t dtypes,
+                            cc_stream_t stream) {
   if (cols <= 0) return 0;
+  CC_REQUIRE(out != nullptr || dz != nullptr, "cc_bias_grad: nothing to compute");
+  CC_REQUIRE(dz_lo == nullptr || (dz != nullptr && !F32(dtypes, 2)),
+             "cc_bias_grad: dz_lo needs a bf16 dz (the high-order term)");
   if (rows <= 0) {
-    if (!beta) {
+    if (!beta && out != nullptr) {
       fill_f32_kernel<<<ew_grid(cols, 256), 256, 0, ST(stream)>>>(out, 0.f, cols);
       CC_CHECK_LAUNCH();
     }
@@ -738,7 +747,7 @@ extern "C" int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t
   }
   return launch_colreduce<3>(mat(dy, lddy, F32(dtypes, 0)), mat(y, ldy, F32(dtypes, 1)), rows, cols,
                              nullptr, nullptr, out, beta, ST(stream), act,
-                             mat(dz, lddz, F32(dtypes, 2)));
+                             mat(dz, lddz, F32(dtypes, 2)), mat(dz_lo, lddz_lo, 0));
 }
 
 extern "C" int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo,

@@ -933,9 +933,11 @@ class Net:
                 # fp32 dL/dy -> bf16 dL/dz = dy * act'(y): the GEMM operand of wgrad / dgrad
                 dz = self._buf(self.dzb, out)[:rows]
                 if out in self.prebn:
-                    ops.act_bwd(dy, A[out], dy, act)              # fp32, in place
+                    # dz as hi + lo (two GEMM segments), and the bias gradient from the fp32
+                    # product, in ONE pass over dy and y (frozen layers: no bias gradient)
                     dz_lo = self._buf(self.split_lo, ("dz", out))[:rows]
-                    ops.split_bf16(dy, dz, dz_lo)
+                    ops.bias_grad(dy, A[out], act, L["db"] if train else None, dz=dz, beta=1,
+                                  dz_lo=dz_lo)
                     dzs = [dz, dz_lo]
                 elif train:
                     # one pass over dy and y: dz for the GEMMs and the bias gradient
@@ -987,9 +989,6 @@ class Net:
                                                 dw, rms=rms)
                     ro += k
                 if train:
-                    if out in self.prebn:
-                        ops.bias_grad(dy, A[out], 0, L["db"], beta=1)   # dy already holds dz (fp32)
-                    # (other layers: done together with dz above)
                     if self.fuse_optimizer and "w16lo" in L:
                         # the wgrad epilogues above just updated this kernel: new low-order term
                         ops.split_bf16(L["w32"], L["w16"], L["w16lo"])

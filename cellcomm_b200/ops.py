@@ -239,13 +239,16 @@ def colsum(x, out32, beta=0):
                                 _mask(x), _stream()))
 
 
-def bias_grad(dy, y, act, out32, dz=None, beta=0):
+def bias_grad(dy, y, act, out32, dz=None, beta=0, dz_lo=None):
     """out32[c] (+)= sum_r dy[r,c] * act'(y[r,c])  (Dense bias gradient from the fp32 gradient);
-    dz (optional): also store dy * act'(y) there (one pass instead of act_bwd + bias_grad)."""
+    dz (optional): also store dy * act'(y) there (one pass instead of act_bwd + bias_grad);
+    dz_lo (optional): and its low-order bf16 term (dz then holds the high-order one).
+    out32 = None: only dz (/ dz_lo) is produced."""
     _req(out32, torch.float32, "out")
+    _req(dz_lo, torch.bfloat16, "dz_lo")
     check(_lib.load().cc_bias_grad(_p(dy), _ld(dy), _p(y), _ld(y), dy.shape[0], dy.shape[1],
-                                   int(act), _p(out32), int(beta), _p(dz), _ld(dz),
-                                   _mask(dy, y, dz), _stream()))
+                                   int(act), _p(out32), int(beta), _p(dz), _ld(dz), _p(dz_lo),
+                                   _ld(dz_lo), _mask(dy, y, dz), _stream()))
 
 
 def split_bf16(x, hi, lo):

@@ -218,11 +218,14 @@ int cc_colsum(const void* x, int64_t ld, int64_t rows, int64_t cols, float* out,
  * (Summing the bf16 dZ instead loses the near-cancelling sums of biases that feed a
  * BatchNormalization.)  dz (optional, NULL to skip): also write dz[r,c] = dy*act'(y), the
  * operand of the wgrad / dgrad GEMMs, in the same pass (replaces a cc_act_bwd launch for
- * trained layers).  beta != 0: out += the sums (the caller zeroed a whole bias region with one
- * fill instead of one per layer).  dtypes: dy, y, dz */
+ * trained layers).  dz_lo (optional, with a bf16 dz): also write the low-order term
+ * bf16(dz - float(bf16(dz))) of the two-term expansion (layers whose dz feeds the GEMMs as
+ * hi + lo: one launch instead of cc_act_bwd + cc_split_bf16 + cc_bias_grad).  out may be NULL
+ * (frozen layers: only dz is wanted).  beta != 0: out += the sums (the caller zeroed a whole
+ * bias region with one fill instead of one per layer).  dtypes: dy, y, dz */
 int cc_bias_grad(const void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t rows,
                  int64_t cols, int32_t act, float* out, int32_t beta, void* dz, int64_t lddz,
-                 int32_t dtypes, cc_stream_t stream);
+                 void* dz_lo, int64_t lddz_lo, int32_t dtypes, cc_stream_t stream);
 /* hi = bf16(x), lo = bf16(x - hi): two-term bf16 expansion of an activation, fed to cc_gemm
  * as two accumulating segments where 8 mantissa bits are too few.  dtypes: x */
 int cc_split_bf16(const void* x, int64_t ldx, void* hi, int64_t ldhi, void* lo, int64_t ldlo,

@@ -83,12 +83,15 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
     _store(dw32, g, beta)
 
 
-def bias_grad(dy, y, act, out32, dz=None, beta=0):
+def bias_grad(dy, y, act, out32, dz=None, beta=0, dz_lo=None):
     yy = y.double()
     d = yy * (1 - yy) if act == ACT_SIGMOID else ((yy > 0).double() if act == ACT_RELU else 1.0)
-    _store(out32, (dy.double() * d).sum(0).float(), beta)
-    if dz is not None:
-        _store(dz, (dy.double() * d).float())
+    v = (dy.double() * d).float()
+    _store(out32, v.double().sum(0).float(), beta)
+    if dz_lo is not None:
+        split_bf16(v, dz, dz_lo)
+    elif dz is not None:
+        _store(dz, v)
 
 
 def split_bf16(x, hi, lo):

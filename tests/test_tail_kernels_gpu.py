@@ -280,6 +280,17 @@ def test_fp32_operands_bias_grad_and_split():
     assert torch.allclose(db, (dy32 * ysig * (1 - ysig)).sum(0), rtol=1e-4, atol=1e-4)
     ops.bias_grad(dy32, ysig, ops.ACT_NONE, db)
     assert torch.allclose(db, dy32.sum(0), rtol=1e-4, atol=1e-4)
+    # one launch for "dz as hi + lo, plus the bias gradient" (accumulating into db), and the
+    # frozen-layer form without a bias gradient: same hi / lo as act_bwd + split_bf16
+    v = dy32 * ysig * (1 - ysig)
+    want_hi, want_lo = ops.alloc2d(rows, cols), ops.alloc2d(rows, cols)
+    ops.split_bf16(v, want_hi, want_lo)
+    for out in (torch.full((cols,), 2.0, device="cuda"), None):
+        zh, zl = ops.alloc2d(rows, cols), ops.alloc2d(rows, cols)
+        ops.bias_grad(dy32, ysig, ops.ACT_SIGMOID, out, dz=zh, beta=1, dz_lo=zl)
+        assert torch.equal(zh, want_hi) and torch.equal(zl, want_lo)
+        if out is not None:
+            assert torch.allclose(out, 2.0 + v.sum(0), rtol=1e-4, atol=1e-4)
     # copy2d as cast + scale + accumulate across dtypes
     acc = torch.ones(rows, cols, device="cuda")
     ops.copy2d(hi, acc, beta=1, scale=2.0)
