@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("rms_lr", c_f32), ("rms_rho", c_f32), ("rms_momentum", c_f32), ("rms_eps", c_f32),
         ("route_world", c_i32), ("route_shard", c_i64), ("route_off0", c_i64),
         ("route_base", vp * 16),
+        ("out16_lo", vp), ("ld16_lo", c_i64),
     ]
 
 

@@ -41,6 +41,8 @@ struct EpiParams {
   bf16* out16;
   long long ld16;
   int beta16;
+  bf16* out16_lo;      // low-order term of a two-term bf16 expansion (out16 = the high-order one)
+  long long ld16_lo;
   float* out32;
   long long ld32;
   int beta32;
@@ -236,6 +238,12 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& e, int r, int 
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < ncols) o[j] = f2bf(e.beta16 ? bf2f(o[j]) + v[j] : v[j]);
+    }
+    if (e.out16_lo != nullptr) {
+      bf16* l = e.out16_lo + (long long)r * e.ld16_lo + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) l[j] = f2bf(v[j] - bf2f(f2bf(v[j])));
     }
   }
 }
@@ -484,6 +492,28 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
         bf16* ot = o + t * step + k;
         *ot = f2bf(beta ? bf2f(*ot) + gv : gv);
       });
+    }
+    if (e.out16_lo != nullptr) {
+      bf16* l = e.out16_lo + (long long)rbase * e.ld16_lo + c;
+      const long long lstep = 4 * e.ld16_lo;
+      if (ncol == 4 && (e.ld16_lo & 3) == 0 && ((c & 3) == 0) && ((((uintptr_t)e.out16_lo) & 7) == 0)) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (t < nrow) {
+            const float4 v = g[t];
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x - bf2f(f2bf(v.x)), v.y - bf2f(f2bf(v.y)));
+            __nv_bfloat162 hi = __floats2bfloat162_rn(v.z - bf2f(f2bf(v.z)), v.w - bf2f(f2bf(v.w)));
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo);
+            u.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(l + t * lstep) = u;
+          }
+        }
+      } else {
+        for_each_valid(g, nrow, ncol, [&](int t, int k, float& gv) {
+          l[t * lstep + k] = f2bf(gv - bf2f(f2bf(gv)));
+        });
+      }
     }
   }
 }
@@ -1374,6 +1404,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
              "cc_gemm: fused RMSprop needs ms and mom");
   CC_REQUIRE(d->route_world >= 0 && d->route_world <= CC_PEER_MAX, "cc_gemm: route_world=%d",
              d->route_world);
+  CC_REQUIRE(d->out16_lo == nullptr || (d->out16 != nullptr && d->beta16 == 0),
+             "cc_gemm: out16_lo needs a plain out16 (the high-order term)");
   if (d->route_world > 0) {
     CC_REQUIRE(d->out32 != nullptr && d->beta32 == 0 && d->workspace == nullptr &&
                    d->rms_p32 == nullptr,
@@ -1548,6 +1580,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.out16 = (bf16*)d->out16;
   e.ld16 = d->ld16;
   e.beta16 = d->beta16;
+  e.out16_lo = (bf16*)d->out16_lo;
+  e.ld16_lo = d->ld16_lo;
   e.out32 = d->out32;
   e.ld32 = d->ld32;
   e.beta32 = d->beta32;

@@ -741,6 +741,21 @@ class Net:
             self._ctx_operands[tid] = ops_
         return ops_
 
+    def _feeds_dense(self, tid, dropout_off):
+        """Is tensor `tid` consumed by a Dense layer -- directly, or (dropout_off: predict mode)
+        through a Dropout, which is then the identity?  Decides whether its producer emits the
+        hi / lo operands."""
+        cache = self._needs_cache.setdefault(("feeds_dense", bool(dropout_off)), {})
+        if tid not in cache:
+            hit = False
+            for n in self.g.nodes:
+                if tid in n["ins"]:
+                    hit = hit or n["kind"] == "dense" or \
+                        (dropout_off and n["kind"] == "dropout"
+                         and self._feeds_dense(n["out"], True))
+            cache[tid] = hit
+        return cache[tid]
+
     def _needs(self, train, want):
         key = (bool(train), tuple(sorted(want)))
         nd = self._needs_cache.get(key)
@@ -812,10 +827,20 @@ class Net:
                     if second and self.device.type != "cuda" and len(segs) + len(second) <= 4:
                         segs += second
                     xs, offs, ws = ([sg[j] for sg in segs] for j in range(3))
+                    hi_lo = None
+                    if (dest32 is y and dest16 is None and out in self.split
+                            and self._feeds_dense(out, dropout == "off")):
+                        # a Dense consumes this fp32 output as hi + lo: the epilogue emits both
+                        # bf16 terms next to the fp32 value (no split pass before the consumer)
+                        hi_lo = (self._buf(self.shadow, out)[:rows],
+                                 self._buf(self.split_lo, out)[:rows])
+                        self._ctx_operands[out] = list(hi_lo)
                     if xs:
-                        ops.dense_fwd(xs, ws, offs, L["b32"], act, out16=dest16, out32=dest32)
+                        ops.dense_fwd(xs, ws, offs, L["b32"], act, out16=dest16, out32=dest32,
+                                      hi_lo=hi_lo)
                     else:
                         ops.bias_act(L["b32"], act, rows, out16=dest16, out32=dest32)
+                        self._ctx_operands.pop(out, None)     # (nothing emitted hi / lo)
                     if copy_out is not None:
                         ops.copy2d(y, copy_out)
                 A[out] = y
@@ -843,6 +868,9 @@ class Net:
                 x = A[node["ins"][0]]
                 if dropout == "off":
                     A[out] = x
+                    src = node["ins"][0]     # predict: the identity; reuse prepared operands
+                    if src in self._ctx_operands and (out in self.split) == (src in self.split):
+                        self._ctx_operands[out] = self._ctx_operands[src]
                 else:
                     y = self._buf(self.act, out)[:rows]
                     if width > 0:

@@ -83,7 +83,7 @@ def reload_env():
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
          alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
-         rms=None, route=None):
+         rms=None, route=None, out16_lo=None):
     lib = _lib.load()
     d = GemmDesc()
     d.M, d.N = int(M), int(N)
@@ -105,6 +105,11 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
     _req(out32, torch.float32, "out32")
     d.out16, d.ld16, d.beta16 = _p(out16), _ld(out16), int(beta16)
     d.out32, d.ld32, d.beta32 = _p(out32), _ld(out32), int(beta32)
+    if out16_lo is not None:
+        _req(out16_lo, torch.bfloat16, "out16_lo")
+        if out16 is None or beta16:
+            raise ValueError("gemm(out16_lo=...): needs a plain bf16 out16 (the high-order term)")
+        d.out16_lo, d.ld16_lo = out16_lo.data_ptr(), _ld(out16_lo)
     if use_ws:
         ws = workspace(a_list[0].device)
         d.workspace, d.workspace_elems = ws.data_ptr(), ws.numel()
@@ -133,7 +138,7 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
     check(lib.cc_gemm(C.byref(d), _stream()))
 
 
-def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
+def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None, hi_lo=None):
     """out = act(sum_s xs[s] @ w16[roff_s : roff_s + xs[s].shape[1], :] + bias).
 
     xs: list of [M, K_s] bf16 (Concatenate segments, consumed without materialising);
@@ -145,7 +150,13 @@ def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
         if out32 is not None:
             raise ValueError("dense_fwd: two fp32 outputs")
         out16, out32 = None, out16
-    gemm(M, N, xs, bs, [x.shape[1] for x in xs], 0, 1, bias=bias, act=act, out16=out16, out32=out32)
+    lo = None
+    if hi_lo is not None:       # (hi, lo): also emit the output's two-term bf16 expansion
+        if out16 is not None:
+            raise ValueError("dense_fwd: hi_lo goes with an fp32 output")
+        out16, lo = hi_lo
+    gemm(M, N, xs, bs, [x.shape[1] for x in xs], 0, 1, bias=bias, act=act, out16=out16, out32=out32,
+         out16_lo=lo)
 
 
 def dense_dgrad(dzs, ws16, out, *, dact_y=None, dact=0, alpha=1.0, beta=0):

@@ -177,6 +177,12 @@ typedef struct cc_gemm_desc {
   int64_t route_shard;   /* elements per rank, multiple of 8 */
   int64_t route_off0;    /* offset of out32[0,0] from the bucket start, multiple of 4 */
   float* route_base[16];
+  /* optional second bf16 output: the low-order term bf16(v - float(bf16(v))) of a two-term
+   * expansion whose high-order term is out16 (fp32 activations that the next Dense consumes
+   * as hi + lo GEMM segments: the producer writes both, no cc_split_bf16 pass).  Needs out16,
+   * beta16 == 0. */
+  void* out16_lo;
+  int64_t ld16_lo;
 } cc_gemm_desc;
 
 int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);

@@ -47,7 +47,7 @@ def _store(dst, v, beta=0):
     dst.copy_(v.to(dst.dtype))
 
 
-def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
+def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None, hi_lo=None):
     ws = list(w16) if isinstance(w16, (list, tuple)) else [w16] * len(xs)
     acc = 0
     for x, w, ro in zip(xs, ws, row_offsets):
@@ -56,6 +56,8 @@ def dense_fwd(xs, w16, row_offsets, bias, act, out16=None, out32=None):
     _store(out16, v)
     if out32 is not None:
         out32.copy_(v)
+    if hi_lo is not None:
+        split_bf16(v, hi_lo[0], hi_lo[1])
 
 
 def dense_dgrad(dzs, ws16, out16, *, dact_y=None, dact=0, alpha=1.0, beta=0):

@@ -1,7 +1,8 @@
-CELLCOMM_BENCH_GEMM_TABLE=gpurun_out/r2_gemm_table_b128_floor.txt python bench.py --batch 128 --small-batch 0 --steps 10 --warmup 3 --no-cpu-baseline --dense-e2e-steps 0 > gpurun_out/r2_bench_b128_floor.json 2> gpurun_out/r2_bench_b128_floor.err; echo "rc=$?"
-head -16 gpurun_out/r2_gemm_table_b128_floor.txt
+python -m pytest tests -m gpu -q --tb=short --maxfail=20 > gpurun_out/r2_tests9.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests9.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench9.json 2> gpurun_out/r2_bench9.err; echo "bench rc=$?" >> gpurun_out/r2_tests9.log
+tail -n 4 gpurun_out/r2_tests9.log
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/r2_bench_b128_floor.json'))
-print('ms', d['ms_per_step'], 'tensor set', d['roofline']['ms_per_step'], 'hbm set', d['roofline_hbm']['ms_per_step'], 'gemm total', d['roofline']['gemm_ms_per_step'])
+d=json.load(open('gpurun_out/r2_bench9.json'))
+print('ms', d['ms_per_step'], 'launches/step', d['gpu_launches']/10, 'tensor', d['roofline']['ms_per_step'], d['roofline']['frac'], 'hbm', d['roofline_hbm']['ms_per_step'], 'b128', d['reference_batch']['ms_per_step'], d['reference_batch']['e2e']['ms_per_step'])
 P
