@@ -288,7 +288,10 @@ def test_fp32_operands_bias_grad_and_split():
     for out in (torch.full((cols,), 2.0, device="cuda"), None):
         zh, zl = ops.alloc2d(rows, cols), ops.alloc2d(rows, cols)
         ops.bias_grad(dy32, ysig, ops.ACT_SIGMOID, out, dz=zh, beta=1, dz_lo=zl)
-        assert torch.equal(zh, want_hi) and torch.equal(zl, want_lo)
+        # (torch and the kernel multiply dy * y * (1 - y) in different orders: the fp32 products
+        # differ in the last bit, which is exactly what the low-order term records)
+        assert (zh.float() - want_hi.float()).abs().max().item() <= 2 ** -8 * v.abs().max().item()
+        assert (zh.float() + zl.float() - v).abs().max().item() <= 2 ** -15 * v.abs().max().item()
         if out is not None:
             assert torch.allclose(out, 2.0 + v.sum(0), rtol=1e-4, atol=1e-4)
     # copy2d as cast + scale + accumulate across dtypes
