@@ -83,12 +83,15 @@ def peaks():
 
 def gemm_traffic():
     """DRAM bytes per launch of the two GEMM sets, from the committed ncu pass over one step
-    (profiles/r01_gemm_traffic.json, written by tools/summarize_traffic.py)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    (profiles/r02_gemm_traffic.json, written by tools/summarize_traffic.py from
+    profiles/r02_ncu_launches_b2048.csv)."""
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
 
 
 # ------------------------------------------------------------------------------ data
