@@ -1,8 +1,8 @@
-python -m pytest tests -m gpu -q --tb=short --maxfail=20 > gpurun_out/r2_tests9.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests9.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench9.json 2> gpurun_out/r2_bench9.err; echo "bench rc=$?" >> gpurun_out/r2_tests9.log
-tail -n 4 gpurun_out/r2_tests9.log
+python -m pytest tests/test_gemm_gpu.py -m gpu -q --tb=line -k "fused_rmsprop or wgrad_with_fused" > gpurun_out/r2_tests10.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests10.log
+tail -n 3 gpurun_out/r2_tests10.log
+python tools/rms_tma_bench.py gpurun_out/r2_rms_wide.jsonl > gpurun_out/r2_rms_wide.log 2>&1
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/r2_bench9.json'))
-print('ms', d['ms_per_step'], 'launches/step', d['gpu_launches']/10, 'tensor', d['roofline']['ms_per_step'], d['roofline']['frac'], 'hbm', d['roofline_hbm']['ms_per_step'], 'b128', d['reference_batch']['ms_per_step'], d['reference_batch']['e2e']['ms_per_step'])
+for l in open('gpurun_out/r2_rms_wide.jsonl'):
+    r=json.loads(l); print(r['K'],r['N'],r['batch'],'tma',r['tma_state'],'nfast',r['nfast'],'wide',r['wide'],round(r['ms'],3),round(r['GB/s']))
 P
