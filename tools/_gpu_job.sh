@@ -1,8 +1,4 @@
-CC_GEMM_RMS_WARPS=12 python -m pytest tests/test_gemm_gpu.py -m gpu -q --tb=line -k "fused_rmsprop or wgrad_with_fused" > gpurun_out/r2_tests11.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests11.log
-tail -n 3 gpurun_out/r2_tests11.log
-python tools/rms_tma_bench.py gpurun_out/r2_rms_w12.jsonl > gpurun_out/r2_rms_w12.log 2>&1
-python - <<'P'
-import json
-for l in open('gpurun_out/r2_rms_w12.jsonl'):
-    r=json.loads(l); print(r['K'],r['N'],r['batch'],'tma',r['tma_state'],'warps',r['epi_warps'],round(r['ms'],3),round(r['GB/s']))
-P
+python -m pytest tests -m gpu -q --tb=short --maxfail=20 > gpurun_out/r2_tests12.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests12.log
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_smoke12.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2_tests12.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench12.json 2> gpurun_out/r2_bench12.err; echo "bench rc=$?" >> gpurun_out/r2_tests12.log
+tail -n 5 gpurun_out/r2_tests12.log; tail -n 1 gpurun_out/r2_smoke12.log
