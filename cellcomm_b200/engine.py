@@ -44,6 +44,11 @@ _DP_SKIP_UPDATE = os.environ.get("CELLCOMM_B200_DP_SKIP_UPDATE", "0") == "1"
 _BUCKET_ELEMS = int(os.environ.get("CELLCOMM_B200_BUCKET_ELEMS", str(48 << 20)))
 # hi + lo bf16 compute copies of the BN-feeding kernels of level-3 networks (the generator)
 _HILO_WEIGHTS = os.environ.get("CELLCOMM_B200_HILO_WEIGHTS", "1") != "0"
+# fused-optimiser mode: Dense kernels of at most this many elements are NOT updated inside their
+# wgrad epilogue (their weight-gradient GEMM has one or two output tiles, i.e. runs on one or two
+# SMs for the whole batch reduction: ~45 us each at batch 2048, ~1.9 ms per step over the ~30
+# narrow layers); they take the split-K wgrad and one flat RMSprop sweep per contiguous range
+_NARROW_ELEMS = int(os.environ.get("CELLCOMM_B200_NARROW_ELEMS", str(1 << 19)))
 
 
 # =========================================================================== graph specs
@@ -365,6 +370,7 @@ class Net:
         self.hp, self.split = self._high_precision_tensors()
         self._alloc_params(generator)
         self._build_buckets()
+        self._find_narrow_layers()
         self.act = {}      # forward activations (bf16; fp32 for tensors in self.hp)
         self.shadow = {}   # bf16 copies of fp32 activations that also feed a GEMM
         self.grad = {}     # activation gradients, always fp32
@@ -548,6 +554,32 @@ class Net:
             flags, f_ptrs, h3 = self.dist.symmetric_zeros(2 * nb * W, torch.int32, self.device)
             self.peer.update(flags=flags, f=f_ptrs, nb=nb)
             self.peer["handles"].append(h3)
+
+    def _find_narrow_layers(self):
+        """Narrow Dense kernels at the head and at the tail of the flat layout (the latents' and
+        the 50-300-wide trunks): `narrow` = their layer indices, `narrow_ranges` = the (at most
+        two) flat ranges one RMSprop sweep each updates in fused-optimiser mode; the tail range
+        runs on through the biases / BN parameters to the end of the buffer."""
+        dense = [(i, L) for i, L in enumerate(self.layers) if L["kind"] == "dense"]
+        small = lambda L: L["K"] * L["ld"] <= _NARROW_ELEMS
+        head = []
+        for i, L in dense:
+            if not small(L):
+                break
+            head.append(i)
+        tail = []
+        for i, L in reversed(dense):
+            if not small(L) or i in head:
+                break
+            tail.append(i)
+        self.narrow = set(head) | set(tail)
+        self.narrow_ranges = []
+        if head:
+            last = self.layers[head[-1]]
+            self.narrow_ranges.append((self.layers[head[0]]["w_off"], last["w_off"] + last["K"] * last["ld"]))
+        tail_start = self.layers[tail[-1]]["w_off"] if tail else self.small_off
+        if self.n_flat > tail_start:
+            self.narrow_ranges.append((tail_start, self.n_flat))
 
     def sync_compute_copy(self):
         """bf16 compute copy (and the low-order terms of the hi + lo kernels) <- fp32 master
@@ -997,7 +1029,7 @@ class Net:
                             pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
                                      if a + b < 2]
                             rms = None
-                            if self.fuse_optimizer:
+                            if self.fuse_optimizer and node["layer"] not in self.narrow:
                                 sl = slice(ro, ro + k)
                                 rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
                                        LR, RHO, MOMENTUM, EPSILON)
@@ -1017,7 +1049,7 @@ class Net:
                                                 dw, rms=rms)
                     ro += k
                 if train:
-                    if self.fuse_optimizer and "w16lo" in L:
+                    if self.fuse_optimizer and "w16lo" in L and node["layer"] not in self.narrow:
                         # the wgrad epilogues above just updated this kernel: new low-order term
                         ops.split_bf16(L["w32"], L["w16"], L["w16lo"])
             elif kind == "softmax":
@@ -1083,10 +1115,13 @@ class Net:
         the Dense kernels were already updated inside their wgrad epilogues (the gradient
         never went to HBM) and only the small tail (biases, BN gamma/beta) is updated here."""
         if self.fuse_optimizer:
-            sl = slice(self.small_off, self.n_flat)
-            if self.n_flat > self.small_off:
+            # the narrow kernels (gradient in g32, written by their split-K wgrad) and the
+            # biases / BN parameters: one flat sweep per contiguous range
+            for a, b in self.narrow_ranges:
+                sl = slice(a, b)
                 ops.rmsprop_step(self.p32[sl], self.p16[sl], self.g32[sl], self.ms[sl],
                                  self.mom[sl], LR, RHO, MOMENTUM, EPSILON)
+                self.refresh_lo(a, b)
             return
         if self.opt_stream is None:
             self._reduce_and_update()
