@@ -54,6 +54,10 @@ struct EpiParams {
   long long rms_ld;
   float rms_lr, rms_rho, rms_momentum, rms_eps;
   int rms_cs;  // evict-first (ld/st.global.cs) hints on the optimiser state stream
+  // blocked optimiser-state layout (cc_gemm_desc.rms_blocked): rms_p32 / rms_ms / rms_mom are
+  // the LAYER's blocked arrays, this GEMM's rows start at layer row rms_row0
+  int rms_blocked;
+  int rms_row0;
   // routed fp32 output (data-parallel wgrad): element `rel` of the bucket goes to the rank that
   // owns it, route_base[owner] + rel (peer-mapped staging slot; own share: local memory)
   int route_world;
@@ -748,6 +752,75 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+// Fused RMSprop on one 32 x 32 accumulator chunk with the optimiser state in the BLOCKED layout
+// (include/cellcomm_b200.h, cc_gemm_desc.rms_blocked): the three fp32 arrays of a layer are
+// stored as 32-row x 32-column blocks of 4 KB, block (rb, cb) at ((rb * ld/32) + cb) * 1024
+// floats, and inside a block element (r, c) at (c/4) * 128 + r * 4 + c % 4 -- the order in which
+// tcgen05.ld 32x32b hands a warp its accumulators (lane = row, registers = columns).  Each of the
+// eight float4 accesses per array then covers 512 contiguous bytes and the chunk one 4 KB block
+// per array, with no shared-memory transpose (the smem it used buys a fourth operand stage)
+// and row-major 128-byte pieces ld * 4 bytes apart replaced by whole DRAM pages.  A GEMM whose
+// first row is not a multiple of 32 in the layer (second Concatenate segment) simply has its
+// lanes wrap into the next block row.  The bf16 compute copy (a TMA operand of the forward
+// GEMMs) and the optional gradient output stay row-major: 64 / 128 bytes per lane.
+__device__ __forceinline__ void rms_blocked_chunk(const EpiParams& e, int lane, int r0, int c0,
+                                                  const uint32_t (&raw)[32]) {
+  const int r = r0 + lane;  // row of this GEMM's output
+  if (r >= e.M) return;
+  const int row = e.rms_row0 + r;  // row of the layer's kernel
+  const long long sb =
+      ((long long)(row >> 5) * (e.rms_ld >> 5) + (c0 >> 5)) * 1024 + (long long)(row & 31) * 4;
+  float* pw = e.rms_p32 + sb;
+  float* ps = e.rms_ms + sb;
+  float* pm = e.rms_mom + sb;
+  float4 w[8], s[8], m[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    w[t] = __ldcs(reinterpret_cast<const float4*>(pw + t * 128));
+    s[t] = __ldcs(reinterpret_cast<const float4*>(ps + t * 128));
+    m[t] = __ldcs(reinterpret_cast<const float4*>(pm + t * 128));
+  }
+  const float rho = e.rms_rho, omr = 1.f - e.rms_rho, mu = e.rms_momentum, lr = e.rms_lr,
+              eps = e.rms_eps;
+  const int nvalid = e.N - c0;  // columns of this chunk inside the matrix (padding: gradient 0)
+  uint32_t h[16];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float g0 = (4 * t + 0 < nvalid) ? __uint_as_float(raw[4 * t + 0]) : 0.f;
+    float g1 = (4 * t + 1 < nvalid) ? __uint_as_float(raw[4 * t + 1]) : 0.f;
+    float g2 = (4 * t + 2 < nvalid) ? __uint_as_float(raw[4 * t + 2]) : 0.f;
+    float g3 = (4 * t + 3 < nvalid) ? __uint_as_float(raw[4 * t + 3]) : 0.f;
+    float4 ss, mm, ww;
+    ss.x = rho * s[t].x + omr * g0 * g0;
+    ss.y = rho * s[t].y + omr * g1 * g1;
+    ss.z = rho * s[t].z + omr * g2 * g2;
+    ss.w = rho * s[t].w + omr * g3 * g3;
+    mm.x = mu * m[t].x + lr * g0 * rsqrtf(ss.x + eps);
+    mm.y = mu * m[t].y + lr * g1 * rsqrtf(ss.y + eps);
+    mm.z = mu * m[t].z + lr * g2 * rsqrtf(ss.z + eps);
+    mm.w = mu * m[t].w + lr * g3 * rsqrtf(ss.w + eps);
+    ww.x = w[t].x - mm.x;
+    ww.y = w[t].y - mm.y;
+    ww.z = w[t].z - mm.z;
+    ww.w = w[t].w - mm.w;
+    __stcs(reinterpret_cast<float4*>(ps + t * 128), ss);
+    __stcs(reinterpret_cast<float4*>(pm + t * 128), mm);
+    __stcs(reinterpret_cast<float4*>(pw + t * 128), ww);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(ww.x, ww.y);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(ww.z, ww.w);
+    h[2 * t] = *reinterpret_cast<uint32_t*>(&lo);
+    h[2 * t + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    if (e.out32 != nullptr)  // the gradient itself (parity tests); row-major, padding stays 0
+      *reinterpret_cast<float4*>(e.out32 + (long long)r * e.ld32 + c0 + 4 * t) =
+          make_float4(g0, g1, g2, g3);
+  }
+  if (e.rms_p16 != nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(e.rms_p16 + (long long)r * e.rms_ld + c0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[t] = make_uint4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+  }
+}
+
 // N_FAST: consecutive tiles walk along N (the contiguous direction of the output / parameter
 // matrix), so the CTAs of one wave cover whole output rows: used by the fused-optimiser wgrad,
 // whose epilogue streams 26 B per element and wants DRAM-page-local bursts.
@@ -761,7 +834,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
 // CTAs' "empty" / "accumulator full" barriers; each CTA drains its own 128 accumulator rows
 // from its own TMEM and reports "accumulator free" to the leader.
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST = false,
-          int CLUSTER = 1, bool PAIR = false>
+          int CLUSTER = 1, bool PAIR = false, bool RMS_DIRECT = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
                                const __grid_constant__ GemmParams p,
@@ -983,7 +1056,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           uint32_t raw[32];
           tmem_ld32(t_row + (uint32_t)c, raw);
           tmem_ld_wait();
-          epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
+          if constexpr (RMS_DIRECT) rms_blocked_chunk(p.epi, lane, m0 + q * 32, n0 + c, raw);
+          else epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
         }
       }
       tcgen05_fence_before();
@@ -1247,21 +1321,21 @@ static int launch_major(const TmaMaps& maps, const GemmParams& p, dim3 grid, boo
   return launch_cfg<BN, STAGES, true, false>(maps, p, grid, st);
 }
 
-template <int BN, int STAGES, int EPI_WARPS, bool PAIR = false>
+template <int BN, int STAGES, int EPI_WARPS, bool PAIR = false, bool RMS_DIRECT = false>
 static constexpr size_t smem_bytes_persistent() {
   return (size_t)STAGES * (BM * BK * 2 + (PAIR ? BN / 2 : BN) * BK * 2) + 8 * (2 * STAGES + 6) + 16 +
-         EPI_WARPS * 32 * EPI_LD * 4 + 1024;
+         (RMS_DIRECT ? 0 : EPI_WARPS * 32 * EPI_LD * 4) + 1024;   // no transpose tiles
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool MATH, int EPI_WARPS, bool N_FAST, int CLUSTER,
-          bool PAIR = false>
+          bool PAIR = false, bool RMS_DIRECT = false>
 static int launch_persistent_one(const TmaMaps& maps, const GemmParams& p, int mt, int nt,
                                  int num_sms, cudaStream_t st) {
   auto kern = gemm_tcgen05_persistent_kernel<BN, STAGES, A_MN, B_MN, MATH, EPI_WARPS, N_FAST, CLUSTER,
-                                             PAIR>;
+                                             PAIR, RMS_DIRECT>;
   static bool attr_set = false;
   static int max_ctas = 0;
-  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS, PAIR>();
+  constexpr size_t smem = smem_bytes_persistent<BN, STAGES, EPI_WARPS, PAIR, RMS_DIRECT>();
   static_assert(smem <= 232448, "shared memory per CTA");
   constexpr int threads = 64 + 32 * EPI_WARPS;
   if (!attr_set) {
@@ -1406,6 +1480,19 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
              d->route_world);
   CC_REQUIRE(d->out16_lo == nullptr || (d->out16 != nullptr && d->beta16 == 0),
              "cc_gemm: out16_lo needs a plain out16 (the high-order term)");
+  if (d->rms_blocked) {
+    CC_REQUIRE(d->rms_p32 != nullptr && d->a_mn_major && d->b_mn_major && d->N > 128 &&
+                   d->alpha == 1.f && d->bias == nullptr && d->act == 0 && d->dact_y == nullptr &&
+                   d->out16 == nullptr && d->beta32 == 0 && d->route_world == 0 &&
+                   d->force_splits <= 1 && (d->force_bn == 0 || d->force_bn == 256),
+               "cc_gemm: rms_blocked is for plain weight-gradient GEMMs (X^T dZ, N > 128)");
+    CC_REQUIRE(d->rms_row0 >= 0 && (d->rms_ld & 31) == 0 &&
+                   ((((uintptr_t)d->rms_p32) | ((uintptr_t)d->rms_ms) | ((uintptr_t)d->rms_mom) |
+                     ((uintptr_t)d->rms_p16) | ((uintptr_t)d->out32)) & 15) == 0 &&
+                   (d->out32 == nullptr || (d->ld32 & 3) == 0),
+               "cc_gemm: rms_blocked needs 16-byte aligned blocks, rms_ld %% 32 == 0 (rms_ld=%lld)",
+               (long long)d->rms_ld);
+  }
   if (d->route_world > 0) {
     CC_REQUIRE(d->out32 != nullptr && d->beta32 == 0 && d->workspace == nullptr &&
                    d->rms_p32 == nullptr,
@@ -1597,6 +1684,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // bit 0: evict-first hints on the optimiser-state stream; bit 3: 256-byte L2 fetch granularity
   // for its loads (bits 1, 2: see the TMA-state epilogue below)
   e.rms_cs = (ENV.rms_cs ? 1 : 0) | (ENV.rms_l2_256 ? 8 : 0);
+  e.rms_blocked = d->rms_blocked;
+  e.rms_row0 = d->rms_row0;
   e.route_world = d->route_world;
   e.route_shard = (unsigned)d->route_shard;
   e.route_off0 = d->route_off0;
@@ -1619,6 +1708,19 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       // (measured, profiles/r02_fused_rmsprop_tma_sweep.jsonl: ahead of the register epilogue
       // while the batch reduction is short -- the reference's batch 128 -- and behind it when
       // the operand ring is long, so the default follows the number of k-blocks)
+      if (d->rms_blocked) {
+        // blocked optimiser state: accumulators go straight from TMEM registers to 4 KB state
+        // blocks (rms_blocked_chunk), no transpose tiles -> four operand stages
+        if (p.cluster == 2)
+          return nfast ? launch_persistent_one<256, 4, true, true, false, 8, true, 2, false, true>(
+                             maps, p, mt, nt, g_num_sms, st)
+                       : launch_persistent_one<256, 4, true, true, false, 8, false, 2, false, true>(
+                             maps, p, mt, nt, g_num_sms, st);
+        return nfast ? launch_persistent_one<256, 4, true, true, false, 8, true, 1, false, true>(
+                           maps, p, mt, nt, g_num_sms, st)
+                     : launch_persistent_one<256, 4, true, true, false, 8, false, 1, false, true>(
+                           maps, p, mt, nt, g_num_sms, st);
+      }
       int use_tma = ENV.rms_tma;
       if (use_tma < 0) use_tma = total <= 4 ? 1 : 0;
       const bool tma_ok =

@@ -48,7 +48,11 @@ _HILO_WEIGHTS = os.environ.get("CELLCOMM_B200_HILO_WEIGHTS", "1") != "0"
 # wgrad epilogue (their weight-gradient GEMM has one or two output tiles, i.e. runs on one or two
 # SMs for the whole batch reduction: ~45 us each at batch 2048, ~1.9 ms per step over the ~30
 # narrow layers); they take the split-K wgrad and one flat RMSprop sweep per contiguous range
-_NARROW_ELEMS = int(os.environ.get("CELLCOMM_B200_NARROW_ELEMS", str(1 << 19)))
+_NARROW_ELEMS = int(os.environ.get("CELLCOMM_B200_NARROW_ELEMS", str(1 << 20)))
+# fused-optimiser mode: keep the fp32 master weights and RMSprop slots of the wide kernels in the
+# BLOCKED layout of cc_gemm_desc.rms_blocked (4 KB blocks in accumulator order) while training;
+# they are converted back to rows whenever anything else reads them (Net._rows)
+_BLOCKED_STATE = os.environ.get("CELLCOMM_B200_BLOCKED_STATE", "1") != "0"
 
 
 # =========================================================================== graph specs
@@ -368,6 +372,8 @@ class Net:
         self.device = device
         self.dist = dist or _NoDist()
         self.hp, self.split = self._high_precision_tensors()
+        self.blockable, self.state_blocked = [], False
+        self._opt_event = None
         self._alloc_params(generator)
         self._build_buckets()
         self._find_narrow_layers()
@@ -408,7 +414,8 @@ class Net:
                 off = (off + 4095) // 4096 * 4096
                 meta.append({"kind": "dense", "K": K, "N": N, "ld": ldn, "w_off": off,
                              "act": lay[3], "in_widths": lay[1]})
-                off += K * ldn
+                # whole 32-row blocks: the blocked optimiser-state layout (Net._state_layout)
+                off += (K + 31) // 32 * 32 * ldn
             else:
                 meta.append({"kind": "bn", "n": lay[1]})
         off = (off + 4095) // 4096 * 4096     # kernel region: shardable across up to 16 ranks
@@ -573,6 +580,11 @@ class Net:
                 break
             tail.append(i)
         self.narrow = set(head) | set(tail)
+        # wide kernels whose fp32 state may live in the blocked layout (not the hi + lo ones:
+        # their low-order term is derived from the row-major master after every update)
+        self.blockable = [i for i, L in dense if i not in self.narrow and i not in self.hilo
+                          and L["K"] > 0 and L["N"] > 128] if _BLOCKED_STATE else []
+        self.state_blocked = False
         self.narrow_ranges = []
         if head:
             last = self.layers[head[-1]]
@@ -581,9 +593,38 @@ class Net:
         if self.n_flat > tail_start:
             self.narrow_ranges.append((tail_start, self.n_flat))
 
+    def _state_layout(self, blocked):
+        """Convert p32 / ms / mom of the `blockable` kernels between rows (the layout every
+        view in `layers`, every flat sweep and every collective assumes) and the blocked layout
+        the fused weight-gradient epilogue streams (ops.state_rows_to_blocked; include/
+        cellcomm_b200.h, cc_gemm_desc.rms_blocked).  The bf16 compute copy, the gradients and
+        everything else are always rows.  One layer at a time: the temporary is one kernel."""
+        blocked = bool(blocked) and bool(self.blockable)
+        if blocked == self.state_blocked:
+            return
+        if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"{self.name}: optimiser-state layout change inside a CUDA graph "
+                               f"capture (convert before capturing)")
+        self._wait_optimizer()
+        for i in self.blockable:
+            L = self.layers[i]
+            R, ld = (L["K"] + 31) // 32 * 32, L["ld"]
+            for buf in (self.p32, self.ms, self.mom):
+                reg = buf[L["w_off"]:L["w_off"] + R * ld]
+                if blocked:
+                    reg.copy_(ops.state_rows_to_blocked(reg.view(R, ld)))
+                else:
+                    reg.copy_(ops.state_blocked_to_rows(reg, R, ld).reshape(-1))
+        self.state_blocked = blocked
+
+    def _rows(self):
+        """fp32 master / slots back in rows before anything but the fused epilogue touches them"""
+        self._state_layout(False)
+
     def sync_compute_copy(self):
         """bf16 compute copy (and the low-order terms of the hi + lo kernels) <- fp32 master
         (after init / set_weights)."""
+        self._rows()
         self.p16.copy_(self.p32)
         self.refresh_lo()
 
@@ -618,6 +659,7 @@ class Net:
         """Creation order; Dense -> kernel[in,out], bias; BN -> gamma, beta, mean, var (host)."""
         self._wait_optimizer()
         self.gather_master()
+        self._rows()
         out = []
         for L in self.layers:
             keys = ("w32", "b32") if L["kind"] == "dense" else (
@@ -627,6 +669,7 @@ class Net:
 
     def set_weights(self, arrays):
         self._wait_optimizer()
+        self._rows()
         it = iter(arrays)
         for L in self.layers:
             keys = ("w32", "b32") if L["kind"] == "dense" else (
@@ -706,6 +749,7 @@ class Net:
         sharded optimiser only keeps each rank's own 1/world of the slots current)."""
         self._wait_optimizer()
         self.gather_slots()
+        self._rows()
         out = []
         for L in self.layers:
             for key in (("w32", "b32") if L["kind"] == "dense" else ("gamma", "beta")):
@@ -715,6 +759,7 @@ class Net:
 
     def set_slots(self, slots):
         self._wait_optimizer()
+        self._rows()
         it = iter(slots)
         for L in self.layers:
             for key in (("w32", "b32") if L["kind"] == "dense" else ("gamma", "beta")):
@@ -965,6 +1010,10 @@ class Net:
         if train and self._bucketed():
             for bk in self.buckets:
                 bk["pending"], bk["launched"] = bk["pieces"], False
+        if train:
+            # wide kernels' fp32 state in the blocked layout while the fused epilogue owns them
+            # (a no-op from the second step on), in rows for every other update path
+            self._state_layout(self.fuse_optimizer)
         if train and self.n_flat > self.small_off:
             # ONE fill for every bias gradient of the network (they lie contiguously behind the
             # kernels in the flat gradient buffer); the per-layer reductions then accumulate
@@ -1028,11 +1077,19 @@ class Net:
                             # all hi/lo cross terms except lo*lo
                             pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
                                      if a + b < 2]
-                            rms = None
+                            rms, row0 = None, None
                             if self.fuse_optimizer and node["layer"] not in self.narrow:
                                 sl = slice(ro, ro + k)
-                                rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
-                                       LR, RHO, MOMENTUM, EPSILON)
+                                if self.state_blocked and node["layer"] in self.blockable:
+                                    # the layer's blocked arrays + this segment's first row
+                                    a = L["w_off"]
+                                    b = a + (L["K"] + 31) // 32 * 32 * L["ld"]
+                                    rms = (self.p32[a:b], L["w16"][sl], self.ms[a:b], self.mom[a:b],
+                                           LR, RHO, MOMENTUM, EPSILON)
+                                    row0 = ro
+                                else:
+                                    rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
+                                           LR, RHO, MOMENTUM, EPSILON)
                             if self._bucketed():
                                 # data parallel: one GEMM per gradient piece, and the piece's
                                 # bucket goes to the side stream as soon as it is complete
@@ -1046,7 +1103,7 @@ class Net:
                             else:
                                 dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
                                 ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs],
-                                                dw, rms=rms)
+                                                dw, rms=rms, rms_row0=row0)
                     ro += k
                 if train:
                     if self.fuse_optimizer and "w16lo" in L and node["layer"] not in self.narrow:
@@ -1400,6 +1457,9 @@ class GraphedStep:
             # warm-up run (allocates lazy buffers, sets kernel attributes, fills the tensor-map
             # cache) on a side stream as torch requires; it is a real training step, so the
             # model / optimiser / RNG state is snapshotted and restored around it
+            for n in eng.nets.values():
+                n._state_layout(n.fuse_optimizer)        # not inside the capture
+            self._layouts = {k: n.state_blocked for k, n in eng.nets.items()}
             snap = eng.snapshot_state()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -1423,6 +1483,8 @@ class GraphedStep:
         """idx: batch row positions (host or device int64); None keeps the current buffer."""
         if idx is not None:
             self.idx.copy_(torch.as_tensor(idx), non_blocking=True)
+        for k, n in self.eng.nets.items():
+            n._state_layout(self._layouts[k])      # e.g. get_weights() put the state back in rows
         self.graph.replay()
         for n in self.eng.nets.values():
             n.mark_updated()          # no Python ran inside the graph (sharded data-parallel update)
@@ -1644,7 +1706,7 @@ class BiGanEngine:
         snap = {"rng": self.rng_counter.clone()}
         for k, n in self.nets.items():
             snap[k] = {"p32": n.p32.clone(), "p16": n.p16.clone(), "ms": n.ms.clone(),
-                       "mom": n.mom.clone(),
+                       "mom": n.mom.clone(), "state_blocked": n.state_blocked,
                        "p16lo": None if n.p16lo is None else n.p16lo.clone(),
                        "bn": [(L["moving_mean"].clone(), L["moving_var"].clone())
                               for L in n.layers if L["kind"] == "bn"]}
@@ -1659,6 +1721,7 @@ class BiGanEngine:
             n.p16.copy_(s["p16"])
             n.ms.copy_(s["ms"])
             n.mom.copy_(s["mom"])
+            n.state_blocked = s["state_blocked"]       # raw copies: the layout they were taken in
             if n.p16lo is not None:
                 n.p16lo.copy_(s["p16lo"])
             for L, (mm, mv) in zip([L for L in n.layers if L["kind"] == "bn"], s["bn"]):

@@ -77,6 +77,7 @@ class LayerView:
         net = self._model._net()
         net._wait_optimizer()
         net.gather_master()      # data parallel: collective, like NetModel.get_weights
+        net._rows()
         L = net.layers[self._index]
         keys = ("w32", "b32") if L["kind"] == "dense" else (
             "gamma", "beta", "moving_mean", "moving_var")
@@ -172,6 +173,7 @@ class NetModel:
     def weight_fingerprint(self):
         """Cheap device-side digest used by BasicBiGan.print_params_changes instead of the
         reference's deep copy of every layer (src/bigan_basic.py:72-81)."""
+        self._net()._rows()      # one summation order whatever layout training left the state in
         p = self._net().p32
         return np.array([float(p.sum()), float((p * p).sum())])
 

@@ -83,7 +83,7 @@ def reload_env():
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
          alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
-         rms=None, route=None, out16_lo=None):
+         rms=None, route=None, out16_lo=None, rms_row0=None):
     lib = _lib.load()
     d = GemmDesc()
     d.M, d.N = int(M), int(N)
@@ -114,7 +114,27 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
         ws = workspace(a_list[0].device)
         d.workspace, d.workspace_elems = ws.data_ptr(), ws.numel()
     d.force_splits, d.force_bn = int(splits), int(bn)
-    if rms is not None:
+    if rms is not None and rms_row0 is not None:
+        # blocked optimiser state (cc_gemm_desc.rms_blocked): p32 / ms / mom are the LAYER's flat
+        # blocked arrays, p16 the row-major [M, N] slice this GEMM updates, rms_row0 its first
+        # layer row
+        p32, p16, ms, mom, lr, rho, momentum, eps = rms
+        _req(p16, torch.bfloat16, "p16")
+        if p16 is None or tuple(p16.shape) != (M, N):
+            raise ValueError("gemm(rms=..., rms_row0=...): needs the [M, N] bf16 copy")
+        ld = _ld(p16)
+        need = (int(rms_row0) + M + 31) // 32 * 32 * ld
+        for t, name in ((p32, "p32"), (ms, "ms"), (mom, "mom")):
+            _req(t, torch.float32, name)
+            if t.dim() != 1 or t.numel() < need:
+                raise ValueError(f"gemm(rms_row0=...): {name} must be the layer's flat blocked array "
+                                 f"of at least {need} elements")
+        d.rms_p32, d.rms_ms, d.rms_mom, d.rms_p16 = p32.data_ptr(), ms.data_ptr(), \
+            mom.data_ptr(), p16.data_ptr()
+        d.rms_ld, d.rms_blocked, d.rms_row0 = ld, 1, int(rms_row0)
+        d.rms_lr, d.rms_rho, d.rms_momentum, d.rms_eps = float(lr), float(rho), float(momentum), \
+            float(eps)
+    elif rms is not None:
         p32, p16, ms, mom, lr, rho, momentum, eps = rms
         for t, name in ((p32, "p32"), (ms, "ms"), (mom, "mom")):
             _req(t, torch.float32, name)
@@ -169,13 +189,27 @@ def dense_dgrad(dzs, ws16, out, *, dact_y=None, dact=0, alpha=1.0, beta=0):
          **kw)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
+def state_rows_to_blocked(rows):
+    """[R, ld] row-major fp32 (R % 32 == 0, ld % 32 == 0) -> the flat blocked order of
+    cc_gemm_desc.rms_blocked: 32 x 32 blocks of 4 KB, inside a block (column group of 4, row,
+    column in group)."""
+    R, ld = rows.shape
+    return rows.reshape(R // 32, 32, ld // 32, 8, 4).permute(0, 2, 3, 1, 4).reshape(-1)
+
+
+def state_blocked_to_rows(flat, R, ld):
+    """Inverse of state_rows_to_blocked -> [R, ld] row-major (a copy)."""
+    return flat.reshape(R // 32, ld // 32, 8, 32, 4).permute(0, 3, 1, 2, 4).reshape(R, ld)
+
+
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
     """dw32[K,N] (+)= x[M,K]^T @ dz[M,N].  x may be a list [hi, lo] (bf16 expansion): the
     terms accumulate as GEMM segments along the batch reduction.
     rms = (p32, p16, ms, mom, lr, rho, momentum, eps): fuse the Keras RMSprop update of that
     [K,N] parameter block into the epilogue (dw32 may then be None: the gradient is consumed
-    in registers and never written)."""
-    K, N = (dw32.shape if dw32 is not None else rms[0].shape)
+    in registers and never written).  With rms_row0 the fp32 state is the layer's BLOCKED
+    arrays (state_rows_to_blocked) and this GEMM's rows start at layer row rms_row0."""
+    K, N = (dw32.shape if dw32 is not None else rms[1 if rms_row0 is not None else 0].shape)
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
     # tiny layers (one or two output tiles, reduction over the whole batch) take the split-K
@@ -183,7 +217,7 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
     # route = (world, shard, off0, bases): the epilogue stores every element of dw32 to the rank
     # that owns it in the sharded optimiser (see cc_gemm_desc.route_*)
     gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta,
-         use_ws=rms is None and route is None, rms=rms, route=route)
+         use_ws=rms is None and route is None, rms=rms, route=route, rms_row0=rms_row0)
 
 
 # --------------------------------------------------------------------------- data

@@ -183,6 +183,19 @@ typedef struct cc_gemm_desc {
    * beta16 == 0. */
   void* out16_lo;
   int64_t ld16_lo;
+  /* optional BLOCKED layout of the fused optimiser's fp32 state (rms_blocked != 0; weight-
+   * gradient GEMMs with N > 128 only).  rms_p32 / rms_ms / rms_mom then point at the LAYER's
+   * arrays (not at this GEMM's row slice), stored as 32-row x 32-column blocks of 4 KB: layer
+   * element (r, c) lives at
+   *     ((r / 32) * (rms_ld / 32) + c / 32) * 1024 + ((c % 32) / 4) * 128 + (r % 32) * 4 + c % 4
+   * floats (rms_ld % 32 == 0; the arrays hold ceil(rows / 32) * 32 rows), which is the order a
+   * warp receives its accumulators from tensor memory, so that every access of the epilogue is
+   * 512 contiguous bytes and each 32 x 32 chunk one DRAM-page-local 4 KB block per array.
+   * rms_row0 is the layer row of this GEMM's row 0 (the row offset of a Concatenate segment;
+   * any value >= 0).  rms_p16 (the bf16 compute copy, a TMA operand elsewhere) and out32 stay
+   * row-major views of this GEMM's own [M, N] slice. */
+  int32_t rms_blocked;
+  int32_t rms_row0;
 } cc_gemm_desc;
 
 int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);

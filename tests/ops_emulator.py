@@ -71,7 +71,17 @@ def dense_dgrad(dzs, ws16, out16, *, dact_y=None, dact=0, alpha=1.0, beta=0):
     _store(out16, acc.float(), beta)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
+def state_rows_to_blocked(rows):
+    """cellcomm_b200.ops.state_rows_to_blocked (the documented index formula, restated)"""
+    R, ld = rows.shape
+    return rows.reshape(R // 32, 32, ld // 32, 8, 4).permute(0, 2, 3, 1, 4).reshape(-1)
+
+
+def state_blocked_to_rows(flat, R, ld):
+    return flat.reshape(R // 32, ld // 32, 8, 32, 4).permute(0, 3, 1, 2, 4).reshape(R, ld)
+
+
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
     assert route is None, "routed outputs need peer memory (GPU only)"
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
@@ -79,7 +89,19 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None):
     for t, d in zip(xs, dzs):
         acc = acc + t.double().t() @ d.double()
     g = acc.float()
-    if rms is not None:
+    if rms is not None and rms_row0 is not None:
+        # blocked fp32 state: the layer's flat arrays; update rows [row0, row0 + K) in place
+        p32, p16, ms, mom, lr, rho, momentum, eps = rms
+        K, N = p16.shape
+        ld = p16.stride(0)
+        R = p32.numel() // ld
+        assert R % 32 == 0 and R * ld == p32.numel() and rms_row0 + K <= R
+        rows = [state_blocked_to_rows(t, R, ld).clone() for t in (p32, ms, mom)]
+        sl = slice(rms_row0, rms_row0 + K)
+        rmsprop_step(rows[0][sl, :N], p16, g, rows[1][sl, :N], rows[2][sl, :N], lr, rho, momentum, eps)
+        for t, r in zip((p32, ms, mom), rows):
+            t.copy_(state_rows_to_blocked(r))
+    elif rms is not None:
         p32, p16, ms, mom, lr, rho, momentum, eps = rms
         rmsprop_step(p32, p16, g, ms, mom, lr, rho, momentum, eps)
     _store(dw32, g, beta)

@@ -299,6 +299,8 @@ def test_checkpoint_resume_continues_the_run_on_the_gpu(tmp_path):
     assert np.allclose(seen_b[0][1], seen_a[2][1], rtol=1e-5, atol=1e-6), (seen_a, seen_b)
     for n in ("G", "E", "D"):
         na, nb = net_a._engine.nets[n], b.network._engine.nets[n]
+        na._rows()
+        nb._rows()
         for ta, tb in ((na.p32, nb.p32), (na.ms, nb.ms), (na.mom, nb.mom)):
             assert float((ta - tb).abs().max()) <= 1e-5 * float(ta.abs().max()) + 1e-7
         assert float((na.p16.float() - nb.p16.float()).abs().max()) <= 2e-2 * float(na.p16.float().abs().max())

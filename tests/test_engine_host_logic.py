@@ -85,6 +85,65 @@ def test_trainings_step_matches_oracle(variant, Z, G, B, fused):
                 _close(a, b.numpy(), rtol=1e-3, atol=1e-4, what=f"{net} weight {i} step {step}")
 
 
+def test_blocked_state_layout_is_invisible_outside_the_fused_epilogue(monkeypatch):
+    """Fused-optimiser runs keep p32 / ms / mom of the wide kernels in the blocked layout
+    (Net._state_layout).  With the narrow-layer threshold lowered so that this small model HAS
+    blockable kernels (incl. two-segment ones whose second segment starts at a row that is not a
+    multiple of 32): two training steps equal the row-major run exactly, get_weights /
+    get_slots / snapshot+restore / set_weights see rows, the layers' row views are valid again
+    after any of them, and the next step converts back."""
+    monkeypatch.setattr(eng, "_NARROW_ELEMS", 4096)
+    variant, Z, G, B = "cont", 3, 1400, 16
+
+    def run(blocked):
+        monkeypatch.setattr(eng, "_BLOCKED_STATE", blocked)
+        orc, e = _pair(variant, Z, G, B, fused=True)
+        assert bool(e.D.blockable) == blocked and bool(e.G.blockable) == blocked
+        if blocked:
+            segs = [e.D.layers[i]["in_widths"] for i in e.D.blockable]
+            assert any(len(w) > 1 and w[0] % 32 for w in segs), segs
+        outs = []
+        for step in range(2):
+            x, z, r = _inputs(variant, Z, G, B, 100 + step)
+            masks = O.make_masks(variant, Z, G, B, 7 + step)
+            e.set_latents(z, r, B)
+            x16 = ops_emulator.alloc2d(B, G)
+            x16.copy_(x)
+            outs.append([float(v) for v in e.train_step(x16, masks)])
+            assert e.D.state_blocked == blocked
+            if step == 0:
+                snap = e.snapshot_state()
+                w_mid = {n: e.nets[n].get_weights() for n in ("G", "E", "D")}   # -> rows
+                assert not e.D.state_blocked
+                for L in e.D.layers:
+                    if L["kind"] == "dense":     # row views valid: p16 is bf16(p32)
+                        assert torch.equal(L["w16"].float(), L["w32"].to(L["w16"].dtype).float())
+        return e, outs, w_mid, snap
+
+    e0, o0, w0, _ = run(False)
+    e1, o1, w1, snap = run(True)
+    assert o0 == o1
+    for n in ("G", "E", "D"):
+        for a, b in zip(w0[n], w1[n]):
+            assert np.array_equal(a, b)
+        for a, b in zip(e0.nets[n].get_weights(), e1.nets[n].get_weights()):
+            assert np.array_equal(a, b)
+        for (a, c), (b, d) in zip(e0.nets[n].get_slots(), e1.nets[n].get_slots()):
+            assert np.array_equal(a, b) and np.array_equal(c, d)
+    # the snapshot was taken in the blocked layout: restoring it brings layout and data back
+    e1.restore_state(snap)
+    assert e1.D.state_blocked
+    for n in ("G", "E", "D"):
+        for a, b in zip(w1[n], e1.nets[n].get_weights()):
+            assert np.array_equal(a, b)
+    # padding rows / columns of the state stay zero through the conversions
+    for i in e1.D.blockable:
+        L = e1.D.layers[i]
+        R = (L["K"] + 31) // 32 * 32
+        reg = e1.D.ms[L["w_off"]:L["w_off"] + R * L["ld"]].view(R, L["ld"])
+        assert float(reg[L["K"]:].abs().sum()) == 0.0 and float(reg[:, L["N"]:].abs().sum()) == 0.0
+
+
 def test_predict_paths_match_oracle():
     variant, Z, G, B = "cont", 3, 120, 10
     orc, e = _pair(variant, Z, G, B)

@@ -303,6 +303,76 @@ def test_fused_rmsprop_epilogue_paths(K, N, B, nfast, mode, monkeypatch):
             assert bool(((rim == 7.0) | (rim == 0.0)).all())
 
 
+@pytest.mark.parametrize("nfast", ["0", "1"])
+@pytest.mark.parametrize("K0,K1,N,B", [(300, 500, 1300, 256), (70, 0, 2049, 96), (1000, 333, 520, 2048),
+                                       (33, 31, 257, 128)])
+def test_fused_rmsprop_blocked_state(K0, K1, N, B, nfast, monkeypatch):
+    """Fused optimiser with the fp32 state in the BLOCKED layout (cc_gemm_desc.rms_blocked): a
+    layer of K0 + K1 rows updated by two weight-gradient GEMMs (Concatenate segments; the second
+    starts at a row that is not a multiple of 32, so its lanes wrap across block rows), ragged
+    N, short and long batch reductions, both rasters, with and without the gradient output.
+    The result, converted back to rows, must equal the row-major register path's (same
+    accumulators, same arithmetic up to FMA contraction); the gradient output is bit-identical;
+    padding rows and padding columns of the state stay zero."""
+    ops = _ops()
+    monkeypatch.setenv("CC_GEMM_RMS_NFAST", nfast)
+    monkeypatch.setenv("CC_GEMM_RMS_TMA", "0")
+    K = K0 + K1
+    R, ld = (K + 31) // 32 * 32, ops.pad_ld(N)
+    lr, rho, mo, eps = 0.0075, 0.85, 0.1, 1e-7
+    gen = torch.Generator().manual_seed(5)
+
+    def rows(scale, positive=False):
+        t = torch.zeros(R, ld)
+        v = torch.rand(K, N, generator=gen) if positive else torch.randn(K, N, generator=gen)
+        t[:K, :N] = v * scale
+        return t.cuda()
+
+    w0, ms0, mom0 = rows(0.05), rows(1e-4, True), rows(1e-3)
+    xs = [_rand(B, k, 90 + i, 0.5) if k else None for i, k in enumerate((K0, K1))]
+    dz = _rand(B, N, 93, 0.01)
+    for with_grad in (False, True):
+        # reference: the row-major register path on the same inputs
+        ref = [t.clone() for t in (w0, ms0, mom0)]
+        ref16 = torch.zeros(R, ld, dtype=torch.bfloat16, device="cuda")
+        refdw = torch.full((R, ld), 7.0, device="cuda")
+        blk = [ops.state_rows_to_blocked(t).contiguous() for t in (w0, ms0, mom0)]
+        assert torch.equal(ops.state_blocked_to_rows(blk[0], R, ld), w0)
+        p16 = torch.full((R, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        dw = torch.full((R, ld), 7.0, device="cuda")
+        ro = 0
+        for x, k in zip(xs, (K0, K1)):
+            if k == 0:
+                continue
+            sl = slice(ro, ro + k)
+            ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), refdw[sl, :N] if with_grad else None,
+                            rms=(ref[0][sl, :N], ref16[sl, :N], ref[1][sl, :N], ref[2][sl, :N],
+                                 lr, rho, mo, eps))
+            ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), dw[sl, :N] if with_grad else None,
+                            rms=(blk[0], p16[sl, :N], blk[1], blk[2], lr, rho, mo, eps), rms_row0=ro)
+            ro += k
+        torch.cuda.synchronize()
+        # same accumulators as the row-major path; the update expressions may be contracted
+        # into FMAs differently by the compiler: a few ulp
+        for b, r_, tol in zip(blk, ref, (1e-7, 1e-12, 1e-8)):
+            got = ops.state_blocked_to_rows(b, R, ld)
+            assert torch.allclose(got, r_, rtol=2e-5, atol=tol), float((got - r_).abs().max())
+            assert float(got[K:].abs().sum()) == 0.0 and float(got[:, N:].abs().sum()) == 0.0
+            assert torch.equal(got == 0, r_ == 0)
+        assert float((p16[:K, :N].float() - ref16[:K, :N].float()).abs().max()) <= 1e-3
+        assert torch.equal(p16[:K, :N], ops.state_blocked_to_rows(blk[0], R, ld)[:K, :N].to(torch.bfloat16))
+        # the bf16 copy is written in whole 32-column chunks: padding columns up to the next
+        # multiple of 32 receive bf16(0) (the engine's padding is zero), nothing beyond, no other row
+        edge = min(ld, (N + 31) // 32 * 32)
+        assert float((p16[:, edge:].float() - 7.0).abs().sum()) == 0.0
+        assert float((p16[K:].float() - 7.0).abs().sum()) == 0.0
+        assert bool(((p16[:K, N:edge] == 7.0) | (p16[:K, N:edge] == 0.0)).all())
+        if with_grad:
+            assert torch.equal(dw[:K, :N], refdw[:K, :N])
+            assert float(dw[:K, N:edge].abs().sum()) == 0.0
+            assert float((dw[:, edge:] - 7.0).abs().sum()) == 0.0 and float((dw[K:] - 7.0).abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize("bn_eff", [128, 160, 192, 224, 256])
 @pytest.mark.parametrize("orient", ["fwd", "dgrad", "wgrad"])
 def test_effective_tile_width(bn_eff, orient, monkeypatch):

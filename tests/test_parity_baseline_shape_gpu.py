@@ -93,7 +93,8 @@ def _check_update(p, k, x16, xo, zo, ro, masks, dmasks, B, *, resync=True):
     ops.fill_f32(p.e.loss_buf, 0.0)
     p.e.substep(k, x16, dmasks)
     p.e.join()
-    torch.cuda.synchronize()
+    net._rows()         # the fused epilogue keeps the wide kernels' fp32 state blocked: back to
+    torch.cuda.synchronize()   # rows before the layer views below are read
     got_loss = float(p.e.loss_buf[SLOT[k]])
     assert abs(got_loss - ref_loss) <= 1e-2 * abs(ref_loss) + 1e-3, \
         f"sub-step {k} (B={B}): loss {got_loss} vs oracle {ref_loss}"
