@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
         ("route_world", c_i32), ("route_shard", c_i64), ("route_off0", c_i64),
         ("route_base", vp * 16),
         ("out16_lo", vp), ("ld16_lo", c_i64),
-        ("rms_blocked", c_i32), ("rms_row0", c_i32),
+        ("rms_blocked", c_i32), ("rms_row0", c_i32), ("rms_p16_lo", vp),
     ]
 
 

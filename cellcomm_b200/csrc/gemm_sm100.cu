@@ -58,6 +58,7 @@ struct EpiParams {
   // the LAYER's blocked arrays, this GEMM's rows start at layer row rms_row0
   int rms_blocked;
   int rms_row0;
+  bf16* rms_p16lo;  // blocked path: low-order bf16 term of the updated weight (hi + lo kernels)
   // routed fp32 output (data-parallel wgrad): element `rel` of the bucket goes to the rank that
   // owns it, route_base[owner] + rel (peer-mapped staging slot; own share: local memory)
   int route_world;
@@ -783,7 +784,7 @@ __device__ __forceinline__ void rms_blocked_chunk(const EpiParams& e, int lane, 
   const float rho = e.rms_rho, omr = 1.f - e.rms_rho, mu = e.rms_momentum, lr = e.rms_lr,
               eps = e.rms_eps;
   const int nvalid = e.N - c0;  // columns of this chunk inside the matrix (padding: gradient 0)
-  uint32_t h[16];
+  uint32_t h[16], hl[16];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     float g0 = (4 * t + 0 < nvalid) ? __uint_as_float(raw[4 * t + 0]) : 0.f;
@@ -810,6 +811,14 @@ __device__ __forceinline__ void rms_blocked_chunk(const EpiParams& e, int lane, 
     __nv_bfloat162 hi = __floats2bfloat162_rn(ww.z, ww.w);
     h[2 * t] = *reinterpret_cast<uint32_t*>(&lo);
     h[2 * t + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    if (e.rms_p16lo != nullptr) {  // hi + lo kernels: lo = bf16(w - float(bf16(w)))
+      __nv_bfloat162 l0 = __floats2bfloat162_rn(ww.x - __uint_as_float(h[2 * t] << 16),
+                                                ww.y - __uint_as_float(h[2 * t] & 0xFFFF0000u));
+      __nv_bfloat162 l1 = __floats2bfloat162_rn(ww.z - __uint_as_float(h[2 * t + 1] << 16),
+                                                ww.w - __uint_as_float(h[2 * t + 1] & 0xFFFF0000u));
+      hl[2 * t] = *reinterpret_cast<uint32_t*>(&l0);
+      hl[2 * t + 1] = *reinterpret_cast<uint32_t*>(&l1);
+    }
     if (e.out32 != nullptr)  // the gradient itself (parity tests); row-major, padding stays 0
       *reinterpret_cast<float4*>(e.out32 + (long long)r * e.ld32 + c0 + 4 * t) =
           make_float4(g0, g1, g2, g3);
@@ -818,6 +827,12 @@ __device__ __forceinline__ void rms_blocked_chunk(const EpiParams& e, int lane, 
     uint4* dst = reinterpret_cast<uint4*>(e.rms_p16 + (long long)r * e.rms_ld + c0);
 #pragma unroll
     for (int t = 0; t < 4; ++t) dst[t] = make_uint4(h[4 * t], h[4 * t + 1], h[4 * t + 2], h[4 * t + 3]);
+  }
+  if (e.rms_p16lo != nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(e.rms_p16lo + (long long)r * e.rms_ld + c0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      dst[t] = make_uint4(hl[4 * t], hl[4 * t + 1], hl[4 * t + 2], hl[4 * t + 3]);
   }
 }
 
@@ -1271,7 +1286,7 @@ static const GemmEnv& gemm_env() {
     e.splits = env_int("CC_GEMM_SPLITS", 0);
     e.persistent = env_int("CC_GEMM_PERSISTENT", 1);
     e.cluster = env_int("CC_GEMM_CLUSTER", 2);
-    e.rms_cluster = env_int("CC_GEMM_RMS_CLUSTER", 1);
+    e.rms_cluster = env_int("CC_GEMM_RMS_CLUSTER", -1);
     e.bn_eff = env_int("CC_GEMM_BN_EFF", 0);
     e.mn_lbo = env_int("CC_GEMM_MN_LBO", 64 * BK * 2);
     e.mn_sbo = env_int("CC_GEMM_MN_SBO", 1024);
@@ -1488,11 +1503,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
                "cc_gemm: rms_blocked is for plain weight-gradient GEMMs (X^T dZ, N > 128)");
     CC_REQUIRE(d->rms_row0 >= 0 && (d->rms_ld & 31) == 0 &&
                    ((((uintptr_t)d->rms_p32) | ((uintptr_t)d->rms_ms) | ((uintptr_t)d->rms_mom) |
-                     ((uintptr_t)d->rms_p16) | ((uintptr_t)d->out32)) & 15) == 0 &&
+                     ((uintptr_t)d->rms_p16) | ((uintptr_t)d->rms_p16_lo) | ((uintptr_t)d->out32)) & 15) == 0 &&
                    (d->out32 == nullptr || (d->ld32 & 3) == 0),
                "cc_gemm: rms_blocked needs 16-byte aligned blocks, rms_ld %% 32 == 0 (rms_ld=%lld)",
                (long long)d->rms_ld);
   }
+  CC_REQUIRE(d->rms_p16_lo == nullptr || d->rms_blocked,
+             "cc_gemm: rms_p16_lo is written by the blocked fused-optimiser epilogue only");
   if (d->route_world > 0) {
     CC_REQUIRE(d->out32 != nullptr && d->beta32 == 0 && d->workspace == nullptr &&
                    d->rms_p32 == nullptr,
@@ -1576,8 +1593,12 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
                       d->route_world > 0);
 
   // 2-CTA clusters (B tile multicast) whenever there are at least two row tiles
+  // (fused optimiser: only when the batch reduction is long enough for the shared B tile to
+  // matter -- at the reference's batch 128 the epilogue is everything and coupling two CTAs'
+  // operand rings only costs, profiles/r02_fused_rmsprop_blocked_state.jsonl)
+  const bool rms_cluster = ENV.rms_cluster < 0 ? total > 8 : ENV.rms_cluster != 0;
   p.cluster = (persistent && mt >= 2 && ENV.cluster == 2 &&
-               (d->rms_p32 == nullptr || ENV.rms_cluster != 0)) ? 2 : 1;
+               (d->rms_p32 == nullptr || rms_cluster)) ? 2 : 1;
   // effective tile width of the persistent kernel: the candidate that minimises
   // waves x (per-tile cost); e.g. N = 3369 at batch 2048 is 224 tiles of 256 (1.51 waves on 148
   // SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each shorter).  The per-tile cost model is
@@ -1686,6 +1707,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.rms_cs = (ENV.rms_cs ? 1 : 0) | (ENV.rms_l2_256 ? 8 : 0);
   e.rms_blocked = d->rms_blocked;
   e.rms_row0 = d->rms_row0;
+  e.rms_p16lo = d->rms_blocked ? (bf16*)d->rms_p16_lo : nullptr;
   e.route_world = d->route_world;
   e.route_shard = (unsigned)d->route_shard;
   e.route_off0 = d->route_off0;

@@ -580,9 +580,8 @@ class Net:
                 break
             tail.append(i)
         self.narrow = set(head) | set(tail)
-        # wide kernels whose fp32 state may live in the blocked layout (not the hi + lo ones:
-        # their low-order term is derived from the row-major master after every update)
-        self.blockable = [i for i, L in dense if i not in self.narrow and i not in self.hilo
+        # wide kernels whose fp32 state may live in the blocked layout
+        self.blockable = [i for i, L in dense if i not in self.narrow
                           and L["K"] > 0 and L["N"] > 128] if _BLOCKED_STATE else []
         self.state_blocked = False
         self.narrow_ranges = []
@@ -1077,10 +1076,11 @@ class Net:
                             # all hi/lo cross terms except lo*lo
                             pairs = [(x, d) for a, x in enumerate(xs) for b, d in enumerate(dzs)
                                      if a + b < 2]
-                            rms, row0 = None, None
+                            rms, row0, lo_out = None, None, None
                             if self.fuse_optimizer and node["layer"] not in self.narrow:
                                 sl = slice(ro, ro + k)
                                 if self.state_blocked and node["layer"] in self.blockable:
+                                    lo_out = L["w16lo"][sl] if "w16lo" in L else None
                                     # the layer's blocked arrays + this segment's first row
                                     a = L["w_off"]
                                     b = a + (L["K"] + 31) // 32 * 32 * L["ld"]
@@ -1103,10 +1103,11 @@ class Net:
                             else:
                                 dw = L["dw"][ro:ro + k] if (rms is None or self.keep_grads) else None
                                 ops.dense_wgrad([p_[0] for p_ in pairs], [p_[1] for p_ in pairs],
-                                                dw, rms=rms, rms_row0=row0)
+                                                dw, rms=rms, rms_row0=row0, rms_lo=lo_out)
                     ro += k
                 if train:
-                    if self.fuse_optimizer and "w16lo" in L and node["layer"] not in self.narrow:
+                    if self.fuse_optimizer and "w16lo" in L and node["layer"] not in self.narrow \
+                            and not (self.state_blocked and node["layer"] in self.blockable):
                         # the wgrad epilogues above just updated this kernel: new low-order term
                         ops.split_bf16(L["w32"], L["w16"], L["w16lo"])
             elif kind == "softmax":

@@ -83,7 +83,7 @@ def reload_env():
 # --------------------------------------------------------------------------- GEMM
 def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=None, dact=0,
          alpha=1.0, out16=None, beta16=0, out32=None, beta32=0, splits=0, bn=0, use_ws=True,
-         rms=None, route=None, out16_lo=None, rms_row0=None):
+         rms=None, route=None, out16_lo=None, rms_row0=None, rms_lo=None):
     lib = _lib.load()
     d = GemmDesc()
     d.M, d.N = int(M), int(N)
@@ -132,9 +132,16 @@ def gemm(M, N, a_list, b_list, k_list, a_mn, b_mn, *, bias=None, act=0, dact_y=N
         d.rms_p32, d.rms_ms, d.rms_mom, d.rms_p16 = p32.data_ptr(), ms.data_ptr(), \
             mom.data_ptr(), p16.data_ptr()
         d.rms_ld, d.rms_blocked, d.rms_row0 = ld, 1, int(rms_row0)
+        if rms_lo is not None:          # low-order bf16 term of the updated weights
+            _req(rms_lo, torch.bfloat16, "rms_lo")
+            if tuple(rms_lo.shape) != (M, N) or _ld(rms_lo) != ld:
+                raise ValueError("gemm(rms_lo=...): must be laid out like the bf16 copy")
+            d.rms_p16_lo = rms_lo.data_ptr()
         d.rms_lr, d.rms_rho, d.rms_momentum, d.rms_eps = float(lr), float(rho), float(momentum), \
             float(eps)
     elif rms is not None:
+        if rms_lo is not None:
+            raise ValueError("gemm(rms_lo=...): only with the blocked state layout (rms_row0)")
         p32, p16, ms, mom, lr, rho, momentum, eps = rms
         for t, name in ((p32, "p32"), (ms, "ms"), (mom, "mom")):
             _req(t, torch.float32, name)
@@ -202,13 +209,14 @@ def state_blocked_to_rows(flat, R, ld):
     return flat.reshape(R // 32, ld // 32, 8, 32, 4).permute(0, 3, 1, 2, 4).reshape(R, ld)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None, rms_lo=None):
     """dw32[K,N] (+)= x[M,K]^T @ dz[M,N].  x may be a list [hi, lo] (bf16 expansion): the
     terms accumulate as GEMM segments along the batch reduction.
     rms = (p32, p16, ms, mom, lr, rho, momentum, eps): fuse the Keras RMSprop update of that
     [K,N] parameter block into the epilogue (dw32 may then be None: the gradient is consumed
     in registers and never written).  With rms_row0 the fp32 state is the layer's BLOCKED
-    arrays (state_rows_to_blocked) and this GEMM's rows start at layer row rms_row0."""
+    arrays (state_rows_to_blocked) and this GEMM's rows start at layer row rms_row0; rms_lo
+    (blocked only) also receives the low-order bf16 term of the updated weights."""
     K, N = (dw32.shape if dw32 is not None else rms[1 if rms_row0 is not None else 0].shape)
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
@@ -217,7 +225,8 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
     # route = (world, shard, off0, bases): the epilogue stores every element of dw32 to the rank
     # that owns it in the sharded optimiser (see cc_gemm_desc.route_*)
     gemm(K, N, xs, dzs, [t.shape[0] for t in xs], 1, 1, out32=dw32, beta32=beta,
-         use_ws=rms is None and route is None, rms=rms, route=route, rms_row0=rms_row0)
+         use_ws=rms is None and route is None, rms=rms, route=route, rms_row0=rms_row0,
+         rms_lo=rms_lo)
 
 
 # --------------------------------------------------------------------------- data

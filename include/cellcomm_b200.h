@@ -196,6 +196,10 @@ typedef struct cc_gemm_desc {
    * row-major views of this GEMM's own [M, N] slice. */
   int32_t rms_blocked;
   int32_t rms_row0;
+  /* blocked layout only, optional: the low-order bf16 term bf16(w - float(bf16(w))) of the
+   * updated weights, row-major [M, N] with leading dimension rms_ld like rms_p16 (kernels the
+   * forward GEMMs consume as hi + lo segments; replaces a cc_split_bf16 pass over the layer) */
+  void* rms_p16_lo;
 } cc_gemm_desc;
 
 int cc_gemm(const cc_gemm_desc* desc, cc_stream_t stream);

@@ -81,7 +81,7 @@ def state_blocked_to_rows(flat, R, ld):
     return flat.reshape(R // 32, ld // 32, 8, 32, 4).permute(0, 3, 1, 2, 4).reshape(R, ld)
 
 
-def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
+def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None, rms_lo=None):
     assert route is None, "routed outputs need peer memory (GPU only)"
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     dzs = list(dz) if isinstance(dz, (list, tuple)) else [dz] * len(xs)
@@ -101,6 +101,9 @@ def dense_wgrad(x, dz, dw32, beta=0, rms=None, route=None, rms_row0=None):
         rmsprop_step(rows[0][sl, :N], p16, g, rows[1][sl, :N], rows[2][sl, :N], lr, rho, momentum, eps)
         for t, r in zip((p32, ms, mom), rows):
             t.copy_(state_rows_to_blocked(r))
+        if rms_lo is not None:
+            w = rows[0][sl, :N]
+            _store(rms_lo, w - w.to(p16.dtype).float())
     elif rms is not None:
         p32, p16, ms, mom, lr, rho, momentum, eps = rms
         rmsprop_step(p32, p16, g, ms, mom, lr, rho, momentum, eps)

@@ -340,6 +340,7 @@ def test_fused_rmsprop_blocked_state(K0, K1, N, B, nfast, monkeypatch):
         assert torch.equal(ops.state_blocked_to_rows(blk[0], R, ld), w0)
         p16 = torch.full((R, ld), 7.0, dtype=torch.bfloat16, device="cuda")
         dw = torch.full((R, ld), 7.0, device="cuda")
+        lo16 = torch.full((R, ld), 7.0, dtype=torch.bfloat16, device="cuda")
         ro = 0
         for x, k in zip(xs, (K0, K1)):
             if k == 0:
@@ -349,7 +350,8 @@ def test_fused_rmsprop_blocked_state(K0, K1, N, B, nfast, monkeypatch):
                             rms=(ref[0][sl, :N], ref16[sl, :N], ref[1][sl, :N], ref[2][sl, :N],
                                  lr, rho, mo, eps))
             ops.dense_wgrad(_dev2d(x, ops), _dev2d(dz, ops), dw[sl, :N] if with_grad else None,
-                            rms=(blk[0], p16[sl, :N], blk[1], blk[2], lr, rho, mo, eps), rms_row0=ro)
+                            rms=(blk[0], p16[sl, :N], blk[1], blk[2], lr, rho, mo, eps), rms_row0=ro,
+                            rms_lo=lo16[sl, :N] if with_grad else None)
             ro += k
         torch.cuda.synchronize()
         # same accumulators as the row-major path; the update expressions may be contracted
@@ -368,6 +370,11 @@ def test_fused_rmsprop_blocked_state(K0, K1, N, B, nfast, monkeypatch):
         assert float((p16[K:].float() - 7.0).abs().sum()) == 0.0
         assert bool(((p16[:K, N:edge] == 7.0) | (p16[:K, N:edge] == 0.0)).all())
         if with_grad:
+            # low-order term of the hi + lo kernels: bf16(w - float(bf16(w))), exactly
+            w_new = ops.state_blocked_to_rows(blk[0], R, ld)[:K, :N]
+            assert torch.equal(lo16[:K, :N], (w_new - p16[:K, :N].float()).to(torch.bfloat16))
+            assert float((lo16[K:].float() - 7.0).abs().sum()) == 0.0
+            assert float((lo16[:, edge:].float() - 7.0).abs().sum()) == 0.0
             assert torch.equal(dw[:K, :N], refdw[:K, :N])
             assert float(dw[:K, N:edge].abs().sum()) == 0.0
             assert float((dw[:, edge:] - 7.0).abs().sum()) == 0.0 and float((dw[K:] - 7.0).abs().sum()) == 0.0
