@@ -59,6 +59,7 @@ struct EpiParams {
   int rms_blocked;
   int rms_row0;
   bf16* rms_p16lo;  // blocked path: low-order bf16 term of the updated weight (hi + lo kernels)
+  int rms_keep_operands;  // blocked path: operand TMA loads carry an L2 evict_last policy
   // routed fp32 output (data-parallel wgrad): element `rel` of the bucket goes to the rank that
   // owns it, route_base[owner] + rel (peer-mapped staging slot; own share: local memory)
   int route_world;
@@ -708,6 +709,33 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// the same loads with an L2 cache policy (operands of the fused-optimiser wgrad: evict_last, so
+// that the 26 B/parameter optimiser stream -- evict_first on its side -- does not push X / dZ
+// out of L2 between the row blocks that re-read them).  CC_GEMM_RMS_KEEP_OPERANDS=1; measured
+// neutral to slightly negative at batch 512 ... 4096 (profiles/r02_fused_rmsprop_blocked_state
+// .jsonl), so off by default.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_pol(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_pol(uint32_t dst, const CUtensorMap* map,
+                                                   uint32_t bar, int c0, int c1, uint16_t mask,
+                                                   uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
@@ -967,6 +995,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   } else if (warp == 0) {
     // ===================== TMA producer =====================
     uint32_t it = 0;
+    const uint64_t keep = (RMS_DIRECT && p.epi.rms_keep_operands) ? l2_policy_evict_last() : 0;
     for (int u = unit0; u < num_units; u += unit_step) {
       const int m0 = unit_m0(u), n0 = unit_n0(u);
       int seg = 0, kb_in_seg = 0;
@@ -979,14 +1008,34 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           const uint32_t b_dst = a_dst + A_BYTES;
           const int k0 = kb_in_seg * BK;
           mbar_expect_tx(full_bar(s), p.stage_tx);
-          if (A_MN) {
+          if (RMS_DIRECT && A_MN && B_MN && keep != 0) {
+            // (the fused-optimiser wgrad: both operands MN-major)
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_pol(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0,
+                              keep);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              if (j >= p.b_boxes) continue;
+              if (CLUSTER == 2) {
+                if ((j & 1) == rank)
+                  tma_load_2d_mc_pol(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s),
+                                     n0 + 64 * j, k0, (uint16_t)3, keep);
+              } else {
+                tma_load_2d_pol(b_dst + j * (64 * BK * 2), &maps.b[seg], full_bar(s), n0 + 64 * j,
+                                k0, keep);
+              }
+            }
+          } else if (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(a_dst + j * (64 * BK * 2), &maps.a[seg], full_bar(s), m0 + 64 * j, k0);
           } else {
             tma_load_2d(a_dst, &maps.a[seg], full_bar(s), k0, m0);
           }
-          if (CLUSTER == 2) {
+          if (RMS_DIRECT && A_MN && B_MN && keep != 0) {
+            // (B loaded above)
+          } else if (CLUSTER == 2) {
             // this CTA's half of the B tile, delivered to both CTAs
             if (B_MN) {
 #pragma unroll
@@ -1271,6 +1320,7 @@ struct GemmEnv {
   int rms_pair;
   int pair;
   int rms_l2_256;
+  int rms_keep;
 };
 static GemmEnv g_env;
 static std::atomic<int> g_env_state{0};   // 0: not loaded
@@ -1302,6 +1352,7 @@ static const GemmEnv& gemm_env() {
     e.rms_pair = env_int("CC_GEMM_RMS_PAIR", 0);
     e.pair = env_int("CC_GEMM_PAIR", 0);
     e.rms_l2_256 = env_int("CC_GEMM_RMS_L2_256", 0);
+    e.rms_keep = env_int("CC_GEMM_RMS_KEEP_OPERANDS", 0);
     g_env = e;
     g_env_state.store(1, std::memory_order_release);
   }
@@ -1708,6 +1759,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   e.rms_blocked = d->rms_blocked;
   e.rms_row0 = d->rms_row0;
   e.rms_p16lo = d->rms_blocked ? (bf16*)d->rms_p16_lo : nullptr;
+  e.rms_keep_operands = ENV.rms_keep;
   e.route_world = d->route_world;
   e.route_shard = (unsigned)d->route_shard;
   e.route_off0 = d->route_off0;
