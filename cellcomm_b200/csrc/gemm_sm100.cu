@@ -1153,28 +1153,76 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
 namespace cc {
 
 // Sum split-K partials and apply the epilogue.  One thread per (row, 32-col chunk).
+// One thread per (row, 4 columns): consecutive lanes read consecutive float4 of a partial row
+// (coalesced) and a 256 x 256 output still spreads over 128 CTAs -- with one thread per 32
+// columns the narrow layers' 24-way split-K sums ran on 16 CTAs and cost more than their GEMMs.
 __global__ void splitk_finalize_kernel(const EpiParams e, const float* __restrict__ partial,
                                        long long partial_ld, long long partial_stride, int splits) {
-  const int chunks = (e.N + 31) / 32;
+  const int groups = (e.N + 3) / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)e.M * chunks) return;
-  const int r = (int)(idx / chunks);
-  const int c0 = (int)(idx % chunks) * 32;
-  float v[32];
+  if (idx >= (long long)e.M * groups) return;
+  const int r = (int)(idx / groups);
+  const int c0 = (int)(idx % groups) * 4;
+  const float* src = partial + (long long)r * partial_ld + c0;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {   // fixed order: bit-reproducible
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(src + (long long)s * partial_stride));
+    a.x += q.x;
+    a.y += q.y;
+    a.z += q.z;
+    a.w += q.w;
+  }
+  float v[4] = {a.x, a.y, a.z, a.w};
+  const int ncols = min(4, e.N - c0);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float* src = partial + (long long)s * partial_stride + (long long)r * partial_ld + c0;
+  for (int j = 0; j < 4; ++j) {
+    float x = v[j] * e.alpha;
+    if (e.bias != nullptr && j < ncols) x += __ldg(e.bias + c0 + j);
+    if (e.act == CC_ACT_SIGMOID) x = sigmoidf_(x);
+    else if (e.act == CC_ACT_RELU) x = fmaxf(x, 0.f);
+    v[j] = x;
+  }
+  if (e.dact != 0) {
+    const bf16* yrow = e.dact_y + (long long)r * e.ld_dact + c0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 q = *reinterpret_cast<const float4*>(src + j);
-      v[j] += q.x;
-      v[j + 1] += q.y;
-      v[j + 2] += q.z;
-      v[j + 3] += q.w;
+    for (int j = 0; j < 4; ++j) {
+      if (j < ncols) {
+        const float y = bf2f(yrow[j]);
+        v[j] *= (e.dact == CC_ACT_SIGMOID) ? y * (1.f - y) : (y > 0.f ? 1.f : 0.f);
+      }
     }
   }
-  epilogue_store32(e, r, c0, v);
+  if (e.out32 != nullptr) {
+    float* o = e.out32 + (long long)r * e.ld32 + c0;
+    if (ncols == 4 && (((uintptr_t)o) & 15) == 0 && !e.beta32) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < ncols) o[j] = e.beta32 ? o[j] + v[j] : v[j];
+    }
+  }
+  if (e.out16 != nullptr) {
+    bf16* o = e.out16 + (long long)r * e.ld16 + c0;
+    if (ncols == 4 && (((uintptr_t)o) & 7) == 0 && !e.beta16) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(o) = u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < ncols) o[j] = f2bf(e.beta16 ? bf2f(o[j]) + v[j] : v[j]);
+    }
+    if (e.out16_lo != nullptr) {
+      bf16* l = e.out16_lo + (long long)r * e.ld16_lo + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < ncols) l[j] = f2bf(v[j] - bf2f(f2bf(v[j])));
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1852,8 +1900,8 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     rc = launch_major<128, 3>(maps, p, grid, a_mn, b_mn, st);
   if (rc) return rc;
   if (splits >= 2) {
-    const long long work = (long long)d->M * ((d->N + 31) / 32);
-    const int threads = 128;
+    const long long work = (long long)d->M * ((d->N + 3) / 4);
+    const int threads = 256;
     splitk_finalize_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(
         p.epi, p.partial, p.partial_ld, p.partial_stride, splits);
     CC_CHECK_LAUNCH();

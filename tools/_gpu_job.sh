@@ -1,4 +1,3 @@
-set -x
-python tools/wgrad_fused_one.py 6738 33694 128,2048 2 --blocked > gpurun_out/r2_blocked_one.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:persistent -o gpurun_out/r2_blocked_full -f python tools/wgrad_fused_one.py 6738 33694 128,2048 2 --blocked > gpurun_out/r2_blocked_ncu.log 2>&1
-tail -3 gpurun_out/r2_blocked_one.log; tail -3 gpurun_out/r2_blocked_ncu.log
+python -m pytest tests/test_gemm_gpu.py tests/test_parity_gpu.py -m gpu -q --tb=short --maxfail=10 > gpurun_out/r2_tests18.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_tests18.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench18.json 2> gpurun_out/r2_bench18.err; echo "bench rc=$?" >> gpurun_out/r2_tests18.log
+tail -n 4 gpurun_out/r2_tests18.log
