@@ -110,16 +110,45 @@ __device__ __forceinline__ void store1(const Mat& m, long long r, long long c, f
 }
 
 // Iterate over [rows, cols] in chunks of 8 consecutive columns; F(row, col0, nvalid).
+// One division per thread, not per chunk: the T threads of the launch form T / cpr "row lanes"
+// of cpr threads each (cpr = chunks per row); a thread keeps its column chunk and walks down
+// the rows.  When a row has more chunks than the launch has threads, the plain grid-stride
+// walk (with its division) is used.
 template <typename F>
 __device__ __forceinline__ void for_each_chunk8(long long rows, long long cols, F f) {
   const long long cpr = (cols + 7) / 8;
-  const long long total = rows * cpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cpr;
-    const long long c0 = (i - r * cpr) * 8;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cpr <= T && cpr < (1ll << 31)) {
+    const unsigned lanes = (unsigned)(T / cpr);
+    const unsigned lane = (unsigned)(tid / cpr);
+    if (lane >= lanes) return;
+    const long long c0 = (tid - (long long)lane * cpr) * 8;
     const int n = (int)min((long long)8, cols - c0);
-    f(r, c0, n);
+    for (long long r = lane; r < rows; r += lanes) f(r, c0, n);
+  } else {
+    const long long total = rows * cpr;
+    for (long long i = tid; i < total; i += T) {
+      const long long r = i / cpr;
+      const long long c0 = (i - r * cpr) * 8;
+      const int n = (int)min((long long)8, cols - c0);
+      f(r, c0, n);
+    }
+  }
+}
+
+// eight consecutive fp32 per-column parameters (BN gamma / beta / mean / rstd): two float4
+// when aligned (c0 is a multiple of 8), scalars at a ragged edge
+__device__ __forceinline__ void load8_param(const float* __restrict__ p, long long c0, int n,
+                                            float (&f)[8]) {
+  if (n == 8 && ((((uintptr_t)(p + c0)) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c0 + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = (i < n) ? __ldg(p + c0 + i) : 0.f;
   }
 }
 
@@ -276,127 +305,147 @@ __global__ void fill_f32_kernel(float* dst, float v, long long n) {
 }
 
 // ------------------------------------------------------------------ column reductions
-// out[c] = sum_r f0(r,c), out[cols + c] = sum_r f1(r,c).  A block of 32x8 threads owns 64
-// columns (two adjacent columns per thread per row) and strides over a slab of rows; slabs
-// combine with atomics only when there is more than one slab (grid.y > 1).
-__device__ __forceinline__ void load_pair(const Mat& m, long long r, long long c, bool c0ok,
-                                          bool c1ok, float& x0, float& x1) {
-  x0 = x1 = 0.f;
+// four adjacent columns of one row (16-byte / 8-byte vector access when whole and aligned)
+__device__ __forceinline__ void load_quad(const Mat& m, long long r, long long c, int nv,
+                                          float (&x)[4]) {
   if (m.f32) {
     const float* p = reinterpret_cast<const float*>(m.p) + r * m.ld + c;
-    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
-      const float2 t = *reinterpret_cast<const float2*>(p);
-      x0 = t.x;
-      x1 = t.y;
+    if (nv == 4 && (m.ld & 3) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      const float4 t = *reinterpret_cast<const float4*>(p);
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
     } else {
-      if (c0ok) x0 = p[0];
-      if (c1ok) x1 = p[1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (i < nv) ? p[i] : 0.f;
     }
   } else {
     const bf16* p = reinterpret_cast<const bf16*>(m.p) + r * m.ld + c;
-    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 3) == 0)) {
-      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-      x0 = t.x;
-      x1 = t.y;
+    if (nv == 4 && (m.ld & 3) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
+      const uint2 t = *reinterpret_cast<const uint2*>(p);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+      x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
     } else {
-      if (c0ok) x0 = bf2f(p[0]);
-      if (c1ok) x1 = bf2f(p[1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (i < nv) ? bf2f(p[i]) : 0.f;
     }
   }
 }
-
-__device__ __forceinline__ void store_pair(const Mat& m, long long r, long long c, bool c0ok,
-                                           bool c1ok, float x0, float x1) {
+__device__ __forceinline__ void store_quad(const Mat& m, long long r, long long c, int nv,
+                                           const float (&x)[4]) {
   if (m.f32) {
     float* p = reinterpret_cast<float*>(m.p) + r * m.ld + c;
-    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
-      *reinterpret_cast<float2*>(p) = make_float2(x0, x1);
+    if (nv == 4 && (m.ld & 3) == 0 && ((((uintptr_t)m.p) & 15) == 0)) {
+      *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
     } else {
-      if (c0ok) p[0] = x0;
-      if (c1ok) p[1] = x1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nv) p[i] = x[i];
     }
   } else {
     bf16* p = reinterpret_cast<bf16*>(m.p) + r * m.ld + c;
-    if (c1ok && (m.ld & 1) == 0 && ((((uintptr_t)m.p) & 3) == 0)) {
-      *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x0, x1);
+    if (nv == 4 && (m.ld & 3) == 0 && ((((uintptr_t)m.p) & 7) == 0)) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(x[2], x[3]);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&lo);
+      t.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p) = t;
     } else {
-      if (c0ok) p[0] = f2bf(x0);
-      if (c1ok) p[1] = f2bf(x1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nv) p[i] = f2bf(x[i]);
     }
   }
 }
 
-// MODE 3 optionally also WRITES dz = dy*act'(y) (the wgrad / dgrad GEMM operand), so a trained
-// Dense layer needs one pass over dy and y instead of act_bwd + bias_grad
+// out[c] = sum_r f0(r,c), out[cols + c] = sum_r f1(r,c).  A block of 32 x 8 threads owns 128
+// columns (four adjacent columns per thread: a warp reads 512 B (fp32) / 256 B (bf16) of a
+// row per instruction) and strides over a slab of rows, four rows' loads in flight per
+// thread; slabs combine with atomics only when there is more than one slab (grid.y > 1).
 template <int MODE>  // 0: x (1 output)  1: x, x^2   2: dy, dy*xhat   3: dy*act'(y) (1 output)
-__global__ void colreduce_kernel(const Mat a, const Mat b, long long rows, long long cols,
-                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                 float* __restrict__ out, int accumulate, int act,
-                                 const Mat dz = Mat{nullptr, 0, 0},
-                                 const Mat dzlo = Mat{nullptr, 0, 0}) {
-  __shared__ float s0[8][64], s1[8][64];
+__global__ void __launch_bounds__(256)
+colreduce_kernel(const Mat a, const Mat b, long long rows, long long cols,
+                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                 float* __restrict__ out, int accumulate, int act,
+                 const Mat dz = Mat{nullptr, 0, 0}, const Mat dzlo = Mat{nullptr, 0, 0}) {
+  __shared__ float s0[8][128], s1[8][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long c = (long long)blockIdx.x * 64 + tx * 2;
+  const long long c = (long long)blockIdx.x * 128 + tx * 4;
   const long long rows_per_slab = (rows + gridDim.y - 1) / gridDim.y;
   const long long r_begin = (long long)blockIdx.y * rows_per_slab;
   const long long r_end = min(rows, r_begin + rows_per_slab);
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  const bool c0ok = c < cols, c1ok = c + 1 < cols;
-  float m0 = 0.f, m1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const int nv = (int)max(0ll, min(4ll, cols - c));
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f};
   if (MODE == 2) {
-    if (c0ok) { m0 = mean[c]; q0 = rstd[c]; }
-    if (c1ok) { m1 = mean[c + 1]; q1 = rstd[c + 1]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < nv) { mu[i] = mean[c + i]; rs[i] = rstd[c + i]; }
   }
-  if (c0ok) {
-    for (long long r = r_begin + ty; r < r_end; r += 8) {
-      float x0, x1;
-      load_pair(a, r, c, c0ok, c1ok, x0, x1);
-      if (MODE == 0) {
-        a0 += x0;
-        a1 += x1;
-      } else if (MODE == 1) {
-        a0 += x0;
-        a1 += x1;
-        b0 += x0 * x0;
-        b1 += x1 * x1;
-      } else if (MODE == 2) {
-        float y0, y1;
-        load_pair(b, r, c, c0ok, c1ok, y0, y1);
-        a0 += x0;
-        a1 += x1;
-        b0 += x0 * ((y0 - m0) * q0);
-        b1 += x1 * ((y1 - m1) * q1);
-      } else {
-        float y0 = 0.f, y1 = 0.f;
-        if (act != 0) load_pair(b, r, c, c0ok, c1ok, y0, y1);
-        const float v0 = x0 * (act == CC_ACT_SIGMOID ? y0 * (1.f - y0) : (act == CC_ACT_RELU ? (y0 > 0.f ? 1.f : 0.f) : 1.f));
-        const float v1 = x1 * (act == CC_ACT_SIGMOID ? y1 * (1.f - y1) : (act == CC_ACT_RELU ? (y1 > 0.f ? 1.f : 0.f) : 1.f));
-        a0 += v0;
-        a1 += v1;
-        if (dz.p != nullptr) store_pair(dz, r, c, c0ok, c1ok, v0, v1);
-        if (dzlo.p != nullptr)   // two-term bf16 expansion of dz: the low-order term
-          store_pair(dzlo, r, c, c0ok, c1ok, v0 - bf2f(f2bf(v0)), v1 - bf2f(f2bf(v1)));
+  const bool need_b = MODE == 2 || (MODE == 3 && act != 0);
+  auto consume = [&](long long r, const float (&x)[4], const float (&y)[4]) {
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc0[i] += x[i];
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc0[i] += x[i]; acc1[i] += x[i] * x[i]; }
+    } else if (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc0[i] += x[i]; acc1[i] += x[i] * ((y[i] - mu[i]) * rs[i]); }
+    } else {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = x[i] * (act == CC_ACT_SIGMOID ? y[i] * (1.f - y[i])
+                                             : (act == CC_ACT_RELU ? (y[i] > 0.f ? 1.f : 0.f) : 1.f));
+        acc0[i] += v[i];
+      }
+      if (dz.p != nullptr) store_quad(dz, r, c, nv, v);
+      if (dzlo.p != nullptr) {  // two-term bf16 expansion of dz: the low-order term
+        float l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[i] = v[i] - bf2f(f2bf(v[i]));
+        store_quad(dzlo, r, c, nv, l);
       }
     }
-  }
-  s0[ty][tx * 2] = a0;
-  s0[ty][tx * 2 + 1] = a1;
-  s1[ty][tx * 2] = b0;
-  s1[ty][tx * 2 + 1] = b1;
-  __syncthreads();
-  if (ty == 0) {
+  };
+  if (nv > 0) {
+    long long r = r_begin + ty;
+    for (; r + 24 < r_end; r += 32) {
+      float x[4][4], y[4][4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int j = tx * 2 + k;
-      const long long cc_ = (long long)blockIdx.x * 64 + j;
-      if (cc_ >= cols) continue;
+      for (int u = 0; u < 4; ++u) {
+        load_quad(a, r + 8 * u, c, nv, x[u]);
+        if (need_b) load_quad(b, r + 8 * u, c, nv, y[u]);
+        else y[u][0] = y[u][1] = y[u][2] = y[u][3] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) consume(r + 8 * u, x[u], y[u]);
+    }
+    for (; r < r_end; r += 8) {
+      float x[4], y[4] = {0.f, 0.f, 0.f, 0.f};
+      load_quad(a, r, c, nv, x);
+      if (need_b) load_quad(b, r, c, nv, y);
+      consume(r, x, y);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s0[ty][tx * 4 + i] = acc0[i];
+    s1[ty][tx * 4 + i] = acc1[i];
+  }
+  __syncthreads();
+  if (ty < 4) {
+    const int j = ty * 32 + tx;
+    const long long cc_ = (long long)blockIdx.x * 128 + j;
+    if (cc_ < cols && out != nullptr) {
       float t0 = 0.f, t1 = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) {
         t0 += s0[y][j];
         t1 += s1[y][j];
       }
-      if (out == nullptr) continue;
       if (gridDim.y > 1 || accumulate) {
         atomicAdd(out + cc_, t0);
         if (MODE == 1 || MODE == 2) atomicAdd(out + cols + cc_, t1);
@@ -413,7 +462,7 @@ static int launch_colreduce(const Mat& a, const Mat& b, long long rows, long lon
                             const float* mean, const float* rstd, float* out, int accumulate,
                             cudaStream_t st, int act = 0, const Mat dz = Mat{nullptr, 0, 0},
                             const Mat dzlo = Mat{nullptr, 0, 0}) {
-  const unsigned gx = (unsigned)((cols + 63) / 64);
+  const unsigned gx = (unsigned)((cols + 127) / 128);
   // enough row slabs to cover ~2 waves of the machine when there are few column blocks
   unsigned gy = 1;
   const unsigned target = 2u * (unsigned)num_sms();
@@ -460,14 +509,17 @@ __global__ void bn_apply_kernel(const Mat x, const Mat y, long long rows, long l
                                 const float* __restrict__ mean, const float* __restrict__ stat,
                                 int infer, float eps) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
-    float f[8];
+    float f[8], mu[8], st[8], ga[8], be[8];
     load8(x, r, c0, n, f);
+    load8_param(mean, c0, n, mu);
+    load8_param(stat, c0, n, st);
+    load8_param(gamma, c0, n, ga);
+    load8_param(beta, c0, n, be);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < n) {
-        const long long c = c0 + i;
-        const float rs = infer ? rsqrtf(stat[c] + eps) : stat[c];
-        f[i] = (f[i] - mean[c]) * (gamma[c] * rs) + beta[c];
+        const float rs = infer ? rsqrtf(st[i] + eps) : st[i];
+        f[i] = (f[i] - mu[i]) * (ga[i] * rs) + be[i];
       }
     }
     store8(y, r, c0, n, f);
@@ -480,15 +532,19 @@ __global__ void bn_bwd_apply_kernel(const Mat dy, const Mat x, const Mat dx, lon
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ sums2, float inv_n) {
   for_each_chunk8(rows, cols, [&](long long r, long long c0, int n) {
-    float g[8], a[8];
+    float g[8], a[8], mu[8], rs[8], ga[8], s0[8], s1[8];
     load8(dy, r, c0, n, g);
     load8(x, r, c0, n, a);
+    load8_param(mean, c0, n, mu);
+    load8_param(rstd, c0, n, rs);
+    load8_param(gamma, c0, n, ga);
+    load8_param(sums2, c0, n, s0);
+    load8_param(sums2 + cols, c0, n, s1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (i < n) {
-        const long long c = c0 + i;
-        const float xhat = (a[i] - mean[c]) * rstd[c];
-        g[i] = gamma[c] * rstd[c] * (g[i] - sums2[c] * inv_n - xhat * sums2[cols + c] * inv_n);
+        const float xhat = (a[i] - mu[i]) * rs[i];
+        g[i] = ga[i] * rs[i] * (g[i] - s0[i] * inv_n - xhat * s1[i] * inv_n);
       }
     }
     store8(dx, r, c0, n, g);
