@@ -1165,12 +1165,24 @@ __global__ void splitk_finalize_kernel(const EpiParams e, const float* __restric
   const int c0 = (int)(idx % groups) * 4;
   const float* src = partial + (long long)r * partial_ld + c0;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {   // fixed order: bit-reproducible
-    const float4 q = __ldcs(reinterpret_cast<const float4*>(src + (long long)s * partial_stride));
-    a.x += q.x;
-    a.y += q.y;
-    a.z += q.z;
-    a.w += q.w;
+  // eight partials' loads in flight, summed in split order (bit-reproducible): with one load
+  // per iteration a 24-way sum was 24 dependent L2 round trips, ~12 us whatever the size
+  for (int s0 = 0; s0 < splits; s0 += 8) {
+    float4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      q[u] = (s0 + u < splits)
+                 ? __ldcs(reinterpret_cast<const float4*>(src + (long long)(s0 + u) * partial_stride))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (s0 + u < splits) {
+        a.x += q[u].x;
+        a.y += q[u].y;
+        a.z += q[u].z;
+        a.w += q[u].w;
+      }
+    }
   }
   float v[4] = {a.x, a.y, a.z, a.w};
   const int ncols = min(4, e.N - c0);

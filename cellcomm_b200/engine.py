@@ -1019,9 +1019,14 @@ class Net:
             ops.fill_f32(self.g32[self.small_off:], 0.0)
 
         out_t = g.output
-        seed = self._buf(self.grad, out_t)[:rows]
-        if g.widths[out_t] > 0 and dout.data_ptr() != seed.data_ptr():
-            ops.copy2d(dout, seed)
+        ext = {}      # gradient tensors read in place instead of from this net's own buffers
+        if dout.dtype == torch.float32 and dout.dim() == 2 and dout.stride(1) == 1 and \
+                dout.shape[1] == g.widths[out_t]:
+            # e.g. dL/d(cell) out of the frozen discriminator's backward: 276 MB at batch 2048
+            # that would otherwise be copied into this net's seed buffer
+            ext[out_t] = dout[:rows]
+        elif g.widths[out_t] > 0:
+            ops.copy2d(dout, self._buf(self.grad, out_t)[:rows])
         state[out_t] = True
         last = g.nodes[-1]
         for node in reversed(g.nodes):
@@ -1029,7 +1034,7 @@ class Net:
             if not state[out] or not needs[out]:
                 continue
             width = g.widths[out]
-            dy = self.grad[out][:rows]
+            dy = ext[out] if out in ext else self.grad[out][:rows]
             if kind == "dense":
                 L = self.layers[node["layer"]]
                 if width == 0:
