@@ -58,7 +58,7 @@ def main():
         json.dump({"step_ms_serialised": total_t / 1e6, "kernels": summary}, f, indent=1)
     traffic = {
         "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the "
-                "launches of one trainings_step (batch 2048) from one ncu pass "
+                "launches of one trainings_step from one ncu pass "
                 "(--clock-control none); source: " + src.split("/")[-1],
         "tensor_launches": sets["tensor"][0],
         "tensor_bytes_per_launch": sets["tensor"][2] / max(sets["tensor"][0], 1),
