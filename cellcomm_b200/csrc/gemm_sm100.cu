@@ -74,6 +74,7 @@ struct GemmParams {
   int kblocks[MAX_SEG];  // k-blocks per segment
   int total_kblocks;
   int kb_per_split;      // k-blocks handled by one blockIdx.z
+  int psplits;           // persistent kernel: k-ranges per tile (work unit = tile x k-range)
   float* partial;        // split-K partials [splits][Mpad][Npad] or nullptr
   long long partial_ld;      // Npad
   long long partial_stride;  // Mpad*Npad
@@ -307,7 +308,8 @@ __device__ __forceinline__ float4 ldcs_256(const float* p) {
 
 template <bool MATH>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage /*32x36*/, int lane,
-                                               int r0, int c0, const uint32_t (&raw)[32]) {
+                                               int r0, int c0, const uint32_t (&raw)[32],
+                                               long long out32_off = 0) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4)
     *reinterpret_cast<uint4*>(stage + lane * EPI_LD + j) =
@@ -461,7 +463,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float* stage 
       }
     }
   } else if (e.out32 != nullptr) {
-    float* o = e.out32 + (long long)rbase * e.ld32 + c;
+    float* o = e.out32 + out32_off + (long long)rbase * e.ld32 + c;   // (+ the split's partial)
     const long long step = 4 * e.ld32;
     if (ncol == 4 && !e.beta32 && (e.ld32 & 3) == 0 && ((c & 3) == 0) &&
         ((((uintptr_t)e.out32) & 15) == 0)) {
@@ -910,10 +912,28 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
   // work units: one tile (CLUSTER 1) or a vertical pair of tiles (CLUSTER 2)
   const int rank = (CLUSTER == 2) ? (int)cluster_ctarank() : 0;
   const int tiles_mu = (tiles_m + CLUSTER - 1) / CLUSTER;
-  const int num_units = tiles_mu * tiles_n;
+  // split-K (weight-streaming regime): a work unit is a tile x one of `psplits` k-ranges; the
+  // tile index varies fastest, so the CTAs running side by side share the same k-slab of A
+  // through L2, and the operand ring / TMEM double buffering run across units like across tiles
+  const int num_tiles = tiles_mu * tiles_n;
+  const int psplits = p.psplits > 1 ? p.psplits : 1;
+  const int num_units = num_tiles * psplits;
   const int unit0 = (int)blockIdx.x / CLUSTER, unit_step = (int)gridDim.x / CLUSTER;
-  auto unit_m0 = [&](int u) { return ((N_FAST ? u / tiles_n : u % tiles_mu) * CLUSTER + rank) * BM; };
-  auto unit_n0 = [&](int u) { return (N_FAST ? u % tiles_n : u / tiles_mu) * p.bn_eff; };
+  auto unit_tile = [&](int u) { return psplits > 1 ? u % num_tiles : u; };
+  auto unit_split = [&](int u) { return psplits > 1 ? u / num_tiles : 0; };
+  auto unit_m0 = [&](int u) {
+    const int t = unit_tile(u);
+    return ((N_FAST ? t / tiles_n : t % tiles_mu) * CLUSTER + rank) * BM;
+  };
+  auto unit_n0 = [&](int u) {
+    const int t = unit_tile(u);
+    return (N_FAST ? t % tiles_n : t / tiles_mu) * p.bn_eff;
+  };
+  // k-blocks [kb0, kb0 + count) of a unit
+  auto unit_kb0 = [&](int u) { return unit_split(u) * p.kb_per_split; };
+  auto unit_nkb = [&](int u) {
+    return psplits > 1 ? min(p.kb_per_split, p.total_kblocks - unit_kb0(u)) : p.total_kblocks;
+  };
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -998,8 +1018,13 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
     const uint64_t keep = (RMS_DIRECT && p.epi.rms_keep_operands) ? l2_policy_evict_last() : 0;
     for (int u = unit0; u < num_units; u += unit_step) {
       const int m0 = unit_m0(u), n0 = unit_n0(u);
-      int seg = 0, kb_in_seg = 0;
-      for (int i = 0; i < nkb; ++i, ++it) {
+      const int nkb_u = unit_nkb(u);
+      int seg = 0, kb_in_seg = unit_kb0(u);   // first k-block of the unit's range -> (segment, offset)
+      while (seg < p.nseg - 1 && kb_in_seg >= p.kblocks[seg]) {
+        kb_in_seg -= p.kblocks[seg];
+        ++seg;
+      }
+      for (int i = 0; i < nkb_u; ++i, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u, 11);
@@ -1071,6 +1096,7 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
       mbar_wait(tempty_bar(acc), aph ^ 1u, 12);  // epilogue has drained this accumulator
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_acc + acc * BN;
+      const int nkb = unit_nkb(u);
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -1121,7 +1147,8 @@ gemm_tcgen05_persistent_kernel(const __grid_constant__ TmaMaps maps,
           tmem_ld32(t_row + (uint32_t)c, raw);
           tmem_ld_wait();
           if constexpr (RMS_DIRECT) rms_blocked_chunk(p.epi, lane, m0 + q * 32, n0 + c, raw);
-          else epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw);
+          else epilogue_chunk<MATH>(p.epi, epi_stage + ew * (32 * EPI_LD), lane, m0 + q * 32, n0 + c, raw,
+                                    (long long)unit_split(u) * p.partial_stride);
         }
       }
       tcgen05_fence_before();
@@ -1381,6 +1408,7 @@ struct GemmEnv {
   int pair;
   int rms_l2_256;
   int rms_keep;
+  int persistent_splitk;
 };
 static GemmEnv g_env;
 static std::atomic<int> g_env_state{0};   // 0: not loaded
@@ -1413,6 +1441,7 @@ static const GemmEnv& gemm_env() {
     e.pair = env_int("CC_GEMM_PAIR", 0);
     e.rms_l2_256 = env_int("CC_GEMM_RMS_L2_256", 0);
     e.rms_keep = env_int("CC_GEMM_RMS_KEEP_OPERANDS", 0);
+    e.persistent_splitk = env_int("CC_GEMM_PERSISTENT_SPLITK", 1);
     g_env = e;
     g_env_state.store(1, std::memory_order_release);
   }
@@ -1487,7 +1516,7 @@ static int launch_persistent_one(const TmaMaps& maps, const GemmParams& p, int m
     }
     attr_set = true;
   }
-  const int units = ((mt + CLUSTER - 1) / CLUSTER) * nt;
+  const int units = ((mt + CLUSTER - 1) / CLUSTER) * nt * (p.psplits > 1 ? p.psplits : 1);
   int grid = units * CLUSTER < max_ctas ? units * CLUSTER : max_ctas / CLUSTER * CLUSTER;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -1699,9 +1728,13 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
     p.kb_per_split = total;
     splits = 1;
   }
+  // split-K inside the persistent kernel (work unit = tile x k-range): the operand ring and the
+  // TMEM double buffer keep running across units, where the one-tile-per-CTA kernel runs one
+  // wave of short-lived CTAs whose prologues and partial-tile stores all coincide
+  const bool psk = splits >= 2 && ENV.persistent != 0 && ENV.persistent_splitk != 0;
   const bool persistent =
-      splits == 1 && (ENV.persistent != 0 || d->rms_p32 != nullptr ||
-                      d->route_world > 0);
+      (splits == 1 || psk) && (ENV.persistent != 0 || d->rms_p32 != nullptr ||
+                               d->route_world > 0);
 
   // 2-CTA clusters (B tile multicast) whenever there are at least two row tiles
   // (fused optimiser: only when the batch reduction is long enough for the shared B tile to
@@ -1715,7 +1748,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // SMs -> 2) but 288 tiles of 192 (1.95 waves -> 2, each shorter).  The per-tile cost model is
   // operand bytes (A is fixed, B scales with the width): the kernels are L2->SM bound.
   int bn_eff = bn;
-  if (persistent && bn == 256 && d->rms_p32 == nullptr) {
+  if (persistent && bn == 256 && d->rms_p32 == nullptr && splits == 1) {
     const int forced = ENV.bn_eff;
     if (forced >= 32 && forced <= 256 && forced % 32 == 0) {
       bn_eff = forced;
@@ -1746,7 +1779,7 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
   // peer's "stage landed" through a relay warp instead of remote complete_tx made it slower
   // still, so the cost sits in the paired MMA's completion path, not in the barrier wiring.
   // Off by default until that is understood; CC_GEMM_PAIR=1 selects it.
-  p.pair = (p.cluster == 2 && bn == 256 && ENV.pair != 0 &&
+  p.pair = (p.cluster == 2 && bn == 256 && ENV.pair != 0 && splits == 1 &&
             (b_mn ? bn_eff % 128 == 0 : bn_eff % 32 == 0)) ? 1 : 0;
   if (p.pair) {
     p.b_boxes = bn_eff / 128;   // per CTA
@@ -1898,6 +1931,30 @@ int gemm_impl(const cc_gemm_desc* d, cudaStream_t st) {
       if (nfast != 0)
         return launch_persistent_cfg<256, 3, true, true, false, 8, true>(maps, p, mt, nt, g_num_sms, st);
       return launch_persistent_cfg<256, 3, true, true, false, 8>(maps, p, mt, nt, g_num_sms, st);
+    }
+    if (splits >= 2) {
+      // k-ranges of a tile go to fp32 partials (raw accumulators, no epilogue math); the
+      // finalize kernel sums them in split order and applies the real epilogue
+      CC_REQUIRE(d->rms_p32 == nullptr, "cc_gemm: fused RMSprop is not available with split-K");
+      GemmParams pp = p;
+      pp.psplits = splits;
+      EpiParams pe{};
+      pe.M = d->M;
+      pe.N = d->N;
+      pe.alpha = 1.f;
+      pe.out32 = p.partial;
+      pe.ld32 = p.partial_ld;
+      pp.epi = pe;
+      int rc = bn == 256
+                   ? launch_persistent_m<256, 4, false>(maps, pp, mt, nt, g_num_sms, a_mn, b_mn, st)
+                   : launch_persistent_m<128, 6, false>(maps, pp, mt, nt, g_num_sms, a_mn, b_mn, st);
+      if (rc) return rc;
+      const long long work = (long long)d->M * ((d->N + 3) / 4);
+      const int threads = 256;
+      splitk_finalize_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, st>>>(
+          p.epi, p.partial, p.partial_ld, p.partial_stride, splits);
+      CC_CHECK_LAUNCH();
+      return 0;
     }
     if (bn == 256) return launch_persistent<256, 4>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);
     return launch_persistent<128, 6>(maps, p, mt, nt, g_num_sms, a_mn, b_mn, st);

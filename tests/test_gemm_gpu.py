@@ -101,6 +101,50 @@ def test_a_mn_b_k_major():
     _check(out, a.float().t() @ b.float().t(), K, False)
 
 
+@pytest.mark.parametrize("persistent", ["1", "0"])
+@pytest.mark.parametrize("orient", ["fwd", "dgrad", "wgrad"])
+@pytest.mark.parametrize("M,N,ks,splits", [(128, 300, (4000,), 5), (300, 100, (700, 1300), 6),
+                                           (520, 1100, (2048, 2048, 2048), 24), (130, 257, (320, 64, 640), 16)])
+def test_split_k_work_units(M, N, ks, splits, orient, persistent, monkeypatch):
+    """Split-K as work units of the persistent kernel (tile x k-range; CC_GEMM_PERSISTENT_SPLITK=1,
+    the default) and in the one-tile-per-CTA kernel (=0): all operand-major combinations,
+    several accumulating segments whose boundaries fall inside a k-range, more k-ranges than
+    k-blocks per segment, several row tiles (2-CTA clusters), N <= 128 (the 128-wide
+    instantiation), bias + activation applied by the finalize pass.  Both kernels sum the same
+    partials in the same order: bit-identical results."""
+    ops = _ops()
+    outs = []
+    for mode in (persistent, "0"):
+        monkeypatch.setenv("CC_GEMM_PERSISTENT_SPLITK", mode)
+        As, Bs, ref = [], [], 0
+        for i, k in enumerate(ks):
+            if orient == "fwd":       # A [M,k] K-major, B [k,N] MN-major
+                a, b = _rand(M, k, 20 + i, 0.3), _rand(k, N, 30 + i, 0.3)
+                ref = ref + a.float() @ b.float()
+            elif orient == "dgrad":   # A [M,k], B [N,k]: both K-major
+                a, b = _rand(M, k, 20 + i, 0.3), _rand(N, k, 30 + i, 0.3)
+                ref = ref + a.float() @ b.float().t()
+            else:                     # A [k,M], B [k,N]: both MN-major
+                a, b = _rand(k, M, 20 + i, 0.3), _rand(k, N, 30 + i, 0.3)
+                ref = ref + a.float().t() @ b.float()
+            As.append(_dev2d(a, ops))
+            Bs.append(_dev2d(b, ops))
+        bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+        out16 = ops.alloc2d(M, N)
+        out32 = torch.full((M, ops.pad_ld(N)), 7.0, device="cuda")[:, :N]
+        a_mn, b_mn = {"fwd": (0, 1), "dgrad": (0, 0), "wgrad": (1, 1)}[orient]
+        ops.gemm(M, N, As, Bs, list(ks), a_mn, b_mn, bias=bias, act=ops.ACT_RELU, out16=out16,
+                 out32=out32, splits=splits)
+        torch.cuda.synchronize()
+        want = torch.relu(ref + bias.cpu())
+        _check(out32, want, sum(ks), False, scale=0.1)
+        _check(out16, want, sum(ks), True, scale=0.1)
+        assert float((out32.as_strided((M, ops.pad_ld(N)), (ops.pad_ld(N), 1))[:, N:] - 7.0).abs().sum()) == 0
+        outs.append(out32.clone())
+    if persistent == "1":
+        assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("splits", [2, 3, 7])
 def test_split_k(splits):
     ops = _ops()
