@@ -265,13 +265,18 @@ def test_evaluate_discriminator_accuracy_matches_oracle():
     assert abs(tp2 - tp) <= 2 and abs(tn2 - tn) <= 2
 
 
-def test_checkpoint_resume_continues_the_run_on_the_gpu(tmp_path):
+@pytest.mark.parametrize("G", [1000, 6000])
+def test_checkpoint_resume_continues_the_run_on_the_gpu(tmp_path, G):
     """Fused optimiser + captured graphs: a run resumed from the Checkpoints interceptor's file
     continues with the same batches, priors and dropout streams; the results equal the
-    uninterrupted run's up to the summation order of the atomics-based reductions."""
+    uninterrupted run's up to the summation order of the atomics-based reductions.  At 6,000
+    genes the wide kernels' fp32 state lives in the blocked device layout between steps
+    (Net._state_layout; incl. two-segment kernels whose second segment starts off a block
+    row): the checkpoint written mid-run, the resumed run and the final state all go through
+    the layout conversions."""
     from cellcomm_b200 import intercepts
     from cellcomm_b200.cell_type_training import CellMatrix
-    N, G, B = 180, 1000, 32
+    N, B = 180, 32
     rng = np.random.default_rng(6)
     dense = ((rng.random((N, G)) < 0.06) * (rng.poisson(1.2, (N, G)) + 1))
     data = CellMatrix.from_dense(dense.astype(np.float64))
@@ -297,6 +302,10 @@ def test_checkpoint_resume_continues_the_run_on_the_gpu(tmp_path):
     b.run(1, lambda it, l: seen_b.append((it, [float(v) for v in l])), start_iteration=start)
     assert [it for it, _ in seen_b] == [2]
     assert np.allclose(seen_b[0][1], seen_a[2][1], rtol=1e-5, atol=1e-6), (seen_a, seen_b)
+    if G == 6000:
+        eng_a = net_a._engine
+        assert eng_a.E.blockable and eng_a.D.blockable and eng_a.G.blockable
+        assert eng_a.D.state_blocked and b.network._engine.D.state_blocked   # left so by the last step
     for n in ("G", "E", "D"):
         na, nb = net_a._engine.nets[n], b.network._engine.nets[n]
         na._rows()
