@@ -412,10 +412,18 @@ class Net:
                 # 4096-element alignment: any layer / 64-row boundary can delimit a gradient
                 # bucket whose 1/world shards (world <= 16) stay 256-element aligned
                 off = (off + 4095) // 4096 * 4096
+                # blocked optimiser-state layout (Net._state_layout): every Concatenate segment
+                # of the kernel gets its own whole 32-row blocks ("virtual rows" seg_vrow[s] =
+                # sum of the earlier segments' rows rounded up to 32), so the region holds
+                # Kv >= K rows; in the row-major layout the rows beyond K are zero padding
+                vrow, v = [], 0
+                for k_s in lay[1]:
+                    vrow.append(v)
+                    v += (k_s + 31) // 32 * 32
                 meta.append({"kind": "dense", "K": K, "N": N, "ld": ldn, "w_off": off,
-                             "act": lay[3], "in_widths": lay[1]})
-                # whole 32-row blocks: the blocked optimiser-state layout (Net._state_layout)
-                off += (K + 31) // 32 * 32 * ldn
+                             "act": lay[3], "in_widths": lay[1], "seg_vrow": vrow,
+                             "Kv": max(v, (K + 31) // 32 * 32)})
+                off += meta[-1]["Kv"] * ldn
             else:
                 meta.append({"kind": "bn", "n": lay[1]})
         off = (off + 4095) // 4096 * 4096     # kernel region: shardable across up to 16 ranks
@@ -607,14 +615,38 @@ class Net:
         self._wait_optimizer()
         for i in self.blockable:
             L = self.layers[i]
-            R, ld = (L["K"] + 31) // 32 * 32, L["ld"]
+            R, ld = L["Kv"], L["ld"]
+            segs = [(ro, vr, k) for ro, vr, k in zip(self._seg_rows(L), L["seg_vrow"],
+                                                     L["in_widths"]) if k > 0]
+            moved = any(ro != vr for ro, vr, _ in segs)
             for buf in (self.p32, self.ms, self.mom):
                 reg = buf[L["w_off"]:L["w_off"] + R * ld]
                 if blocked:
-                    reg.copy_(ops.state_rows_to_blocked(reg.view(R, ld)))
+                    rows = reg.view(R, ld)
+                    if moved:     # every segment to its own block-aligned virtual rows
+                        virt = torch.zeros_like(rows)
+                        for ro, vr, k in segs:
+                            virt[vr:vr + k] = rows[ro:ro + k]
+                        rows = virt
+                    reg.copy_(ops.state_rows_to_blocked(rows))
                 else:
-                    reg.copy_(ops.state_blocked_to_rows(reg, R, ld).reshape(-1))
+                    virt = ops.state_blocked_to_rows(reg, R, ld)
+                    if moved:
+                        rows = torch.zeros_like(virt)
+                        for ro, vr, k in segs:
+                            rows[ro:ro + k] = virt[vr:vr + k]
+                        virt = rows
+                    reg.copy_(virt.reshape(-1))
         self.state_blocked = blocked
+
+    @staticmethod
+    def _seg_rows(L):
+        """first kernel row of every Concatenate segment in the row-major layout"""
+        out, ro = [], 0
+        for k in L["in_widths"]:
+            out.append(ro)
+            ro += k
+        return out
 
     def _rows(self):
         """fp32 master / slots back in rows before anything but the fused epilogue touches them"""
@@ -1088,10 +1120,10 @@ class Net:
                                     lo_out = L["w16lo"][sl] if "w16lo" in L else None
                                     # the layer's blocked arrays + this segment's first row
                                     a = L["w_off"]
-                                    b = a + (L["K"] + 31) // 32 * 32 * L["ld"]
+                                    b = a + L["Kv"] * L["ld"]
                                     rms = (self.p32[a:b], L["w16"][sl], self.ms[a:b], self.mom[a:b],
                                            LR, RHO, MOMENTUM, EPSILON)
-                                    row0 = ro
+                                    row0 = L["seg_vrow"][seg_index]   # block-aligned
                                 else:
                                     rms = (L["w32"][sl], L["w16"][sl], L["ms_w"][sl], L["mom_w"][sl],
                                            LR, RHO, MOMENTUM, EPSILON)

@@ -139,7 +139,8 @@ def test_blocked_state_layout_is_invisible_outside_the_fused_epilogue(monkeypatc
     # padding rows / columns of the state stay zero through the conversions
     for i in e1.D.blockable:
         L = e1.D.layers[i]
-        R = (L["K"] + 31) // 32 * 32
+        R = L["Kv"]
+        assert all(v % 32 == 0 for v in L["seg_vrow"])
         reg = e1.D.ms[L["w_off"]:L["w_off"] + R * L["ld"]].view(R, L["ld"])
         assert float(reg[L["K"]:].abs().sum()) == 0.0 and float(reg[:, L["N"]:].abs().sum()) == 0.0
 

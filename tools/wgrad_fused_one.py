@@ -1,5 +1,5 @@
 """Profiling target: the fused-RMSprop wgrad GEMM on one layer shape.
-    python tools/wgrad_fused_one.py K N batch[,batch...] [iters] [--blocked]"""
+    python tools/wgrad_fused_one.py K N batch[,batch...] [iters] [--blocked] [--row0=R]"""
 import os
 import sys
 
@@ -10,17 +10,18 @@ import torch  # noqa: E402
 from cellcomm_b200 import ops  # noqa: E402
 
 blocked = "--blocked" in sys.argv
+row0_arg = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("--row0=")), 0)
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]
 K, N = int(argv[0]), int(argv[1])
 batches = [int(v) for v in argv[2].split(",")]
 iters = int(argv[3]) if len(argv) > 3 else 3
 ld = ops.pad_ld(N)
-K32 = (K + 31) // 32 * 32
+K32 = (K + row0_arg + 31) // 32 * 32      # the layer: row0 rows of another segment first
 mk = lambda dt=torch.float32: torch.zeros(K32, ld, dtype=dt, device="cuda")[:K, :N]
 p16 = mk(torch.bfloat16)
 if blocked:     # the layer's flat blocked state arrays (cc_gemm_desc.rms_blocked)
     flat = lambda: torch.zeros(K32 * ld, device="cuda")
-    rms, row0 = (flat(), p16, flat(), flat(), 0.0075, 0.85, 0.1, 1e-7), 0
+    rms, row0 = (flat(), p16, flat(), flat(), 0.0075, 0.85, 0.1, 1e-7), row0_arg
 else:
     rms, row0 = (mk(), p16, mk(), mk(), 0.0075, 0.85, 0.1, 1e-7), None
 for B in batches:
