@@ -145,6 +145,23 @@ def test_blocked_state_layout_is_invisible_outside_the_fused_epilogue(monkeypatc
         assert float(reg[L["K"]:].abs().sum()) == 0.0 and float(reg[:, L["N"]:].abs().sum()) == 0.0
 
 
+def test_blocked_layout_index_formula():
+    """ops.state_rows_to_blocked implements the element order documented for
+    cc_gemm_desc.rms_blocked (include/cellcomm_b200.h): element (r, c) of a [R, ld] array at
+    ((r/32) * (ld/32) + c/32) * 1024 + ((c%32)/4) * 128 + (r%32) * 4 + c%4; the emulator's
+    restatement agrees and the inverse restores the rows."""
+    from cellcomm_b200 import ops as real_ops
+    R, ld = 96, 192
+    rows = torch.arange(R * ld, dtype=torch.float32).reshape(R, ld)
+    flat = real_ops.state_rows_to_blocked(rows)
+    assert torch.equal(flat, ops_emulator.state_rows_to_blocked(rows))
+    r = torch.arange(R).view(-1, 1).expand(R, ld)
+    c = torch.arange(ld).view(1, -1).expand(R, ld)
+    idx = ((r // 32) * (ld // 32) + c // 32) * 1024 + ((c % 32) // 4) * 128 + (r % 32) * 4 + c % 4
+    assert torch.equal(flat[idx.reshape(-1)], rows.reshape(-1))
+    assert torch.equal(real_ops.state_blocked_to_rows(flat, R, ld), rows)
+
+
 def test_predict_paths_match_oracle():
     variant, Z, G, B = "cont", 3, 120, 10
     orc, e = _pair(variant, Z, G, B)
